@@ -1,0 +1,155 @@
+/*
+ * l2o_b200 — C-ABI of the B200-native coordinate-wise LSTM learned-optimizer engine.
+ *
+ * The reference (VITA-Group/Open-L2O, L2O-DM / L2O-RNNProp) is pure Python/TensorFlow and has no
+ * FFI; the seam this library sits behind is the reference's own operator surface.  Each entry point
+ * cites the reference code it replaces (DM/ = "Model_Free_L2O/L2O-DM and L2O-RNNProp/"):
+ *
+ *   l2o_net_create / l2o_net_destroy    networks.factory + StandardDeepLSTM.__init__   DM/networks.py:34-44,157-205
+ *   l2o_theta_count / l2o_theta_layout  snt.get_variables_in_module order              DM/networks.py:47-62
+ *   l2o_state_floats                    Network.initial_state_for_inputs               DM/networks.py:234-236,273-276
+ *   l2o_step                            delta, state' = net(g, state)  (one time step) DM/networks.py:207-232,254-271,287-300
+ *                                       + RNNProp Adam features                        DM/meta_rnnprop_train.py:383-388
+ *                                       + x_next = x + delta                           DM/meta.py:352-353
+ *   l2o_unroll_fwd                      the tf.while_loop body x T                     DM/meta.py:338-376
+ *                                       imitation unroll                               DM/meta_dm_train.py:463-480
+ *   l2o_unroll_bwd                      tf.gradients(loss, theta) through that loop    DM/meta.py:412 (BPTT)
+ *   l2o_adam_step                       tf.train.AdamOptimizer(lr).minimize            DM/meta.py:411-413
+ *   l2o_log_and_sign                    preprocess.LogAndSign                          DM/preprocess.py:52-70
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); no hidden
+ * allocation; `stream` is a cudaStream_t passed as void*; every entry returns 0 or a negative
+ * L2O_E_* code and never throws; calls are re-entrant per (device, stream).  All tensors fp32 except
+ * the accumulators `fx`, `imit_loss`, `dtheta` which are fp64 (order-independent atomics).
+ *
+ * Layouts (row-major, N = number of coordinates):
+ *   state arena  : for layer l (size H_l):  h_l [N][H_l] then c_l [N][H_l], layers concatenated
+ *                  == the reference's tuple over layers of (hidden, cell) tensors [N, H_l].
+ *   theta        : flat, Sonnet variable order: [input_projection/w [n_in,F], /b [F],]
+ *                  lstm_1/w_gates [F+H1,4H1], lstm_1/b_gates [4H1], lstm_2/w_gates [H1+H2,4H2],
+ *                  lstm_2/b_gates [4H2], linear/w [top,1], linear/b [1]; gate column order i|j|f|o.
+ *   sequences    : [T][N] time-major; RNNProp feature sequences [T][2][N] (m~ then g~).
+ *   ckpt         : [T+1] state arenas; slot t = state BEFORE step t; slot T = final state.
+ */
+#ifndef L2O_B200_H_
+#define L2O_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L2O_OK 0
+#define L2O_E_INVALID (-1)      /* bad argument (NULL where required, n<0, T<0 ...) */
+#define L2O_E_UNSUPPORTED (-2)  /* net shape / mode not compiled into this build */
+#define L2O_E_CUDA (-3)         /* CUDA runtime error (see l2o_last_cuda_error) */
+#define L2O_E_NOMEM (-4)
+
+#define L2O_PRE_IDENTITY 0 /* tf.identity            DM/networks.py:188,221 */
+#define L2O_PRE_LOGSIGN 1  /* preprocess.LogAndSign  DM/preprocess.py:42-70 */
+#define L2O_PRE_FC 2       /* Linear(dim)+ELU        DM/networks.py:180-183,219 */
+
+#define L2O_OPT_NONE 0
+#define L2O_OPT_RASTRIGIN_SEP 1  /* f = fscale*sum(0.5(x-a)^2 - alpha*b*cos(2 pi x) + alpha)   DM/problems.py:177-213, A=I */
+#define L2O_OPT_QUADRATIC_DIAG 2 /* f = fscale*sum((a*x-b)^2)                                   DM/problems.py:73-101, W diagonal */
+
+#define L2O_ENGINE_AUTO 0
+#define L2O_ENGINE_FFMA 1   /* exact-fp32 CUDA-core kernels */
+#define L2O_ENGINE_TC 2     /* tcgen05 (3xTF32 error-compensated) kernels */
+
+typedef struct l2o_net* l2o_handle;
+
+typedef struct {
+  int32_t n_layers;    /* 0, 1 or 2 */
+  int32_t hidden[2];   /* LSTM sizes */
+  int32_t preprocess;  /* L2O_PRE_* */
+  int32_t n_in;        /* 1: net(g, s) ; 2: RNNprop net(m~, g~, s) */
+  int32_t fc_dim;      /* L2O_PRE_FC: projection width */
+  float logsign_k;     /* L2O_PRE_LOGSIGN */
+  float scale;         /* output scale                DM/networks.py:229-232 */
+  int32_t tanh_output; /* 1: tanh(linear)*scale       DM/networks.py:229-230 */
+} l2o_net_desc;
+
+typedef struct {
+  int64_t n;
+  const float* theta;
+  const float* in0;     /* [n] g (or m~ when n_in==2 and m==NULL) */
+  const float* in1;     /* [n] g~ (n_in==2, operator surface) or NULL */
+  float* m;             /* [n] in/out Adam first moment: non-NULL selects the fused RNNProp feature mode */
+  float* v;             /* [n] in/out */
+  float beta1, beta2;
+  float p;              /* float(step + t)            DM/meta_rnnprop_train.py:384,386 */
+  const float* state_in;/* state arena */
+  float* state_out;     /* may alias state_in */
+  float* x;             /* optional [n], x += delta */
+  float* delta;         /* optional [n] */
+  float* feat_out;      /* optional [2][n]: (m~, g~) actually fed to the net (recorded for BPTT) */
+} l2o_step_args;
+
+typedef struct {
+  int64_t n;
+  int32_t T;
+  const float* theta;
+  const float* in_seq;  /* [T][n_in][n] pre-recorded net inputs, or NULL when opt_kind != NONE */
+  int32_t opt_kind;     /* L2O_OPT_*: gradient evaluated in-kernel from x */
+  const float* opt_a;
+  const float* opt_b;
+  float opt_alpha;
+  float opt_fscale;
+  float* x;             /* [n] in/out (required for in-kernel optimizees; optional otherwise) */
+  float* state;         /* state arena in/out (S_0 -> S_T) */
+  float* ckpt;          /* optional [T+1] arenas: slots 0..T written (slot 0 = S_0 copy) */
+  float* m;             /* fused RNNProp feature mode (with opt_kind != NONE or in_seq = raw g [T][n]) */
+  float* v;
+  float beta1, beta2;
+  int32_t step0;        /* p = float(step0 + t)       DM/util.py:59-60 */
+  float* g_rec;         /* optional [T+1][n]: raw gradients g_0..g_T (g_T at x_T) for the lambda suffix sums */
+  float* feat_rec;      /* optional [T][2][n]: (m~, g~) per step */
+  double* fx;           /* optional [T+1]: fx[t] += f(x_t) (in-kernel optimizees) */
+  float* delta_seq;     /* optional [T][n] */
+  const float* labels;  /* optional [T][n]: imitation targets      DM/meta_dm_train.py:472-475 */
+  double* imit_loss;    /* += sum_t 0.5*sum((label-delta)^2)/n_total */
+  int64_t n_total;
+} l2o_unroll_args;
+
+typedef struct {
+  int64_t n;
+  int32_t T;
+  const float* theta;
+  const float* in_seq;  /* [T][n_in][n] what the net was fed (g_rec rows 0..T-1, feat_rec, or the imitation inputs) */
+  const float* ckpt;    /* [T+1] arenas (slots 0..T-1 read) */
+  const float* g_rec;   /* [T+1][n] raw gradients -> dDelta_t = sum_{tau>t} g_tau ; NULL in imitation mode */
+  const float* labels;  /* imitation mode: dDelta_t = (delta_t - label_t)/n_total */
+  int64_t n_total;
+  double* dtheta;       /* [P] += dL/dtheta */
+} l2o_bwd_args;
+
+int l2o_net_create(l2o_handle* out, const l2o_net_desc* desc);
+void l2o_net_destroy(l2o_handle h);
+int l2o_net_set_engine(l2o_handle h, int32_t engine);
+int64_t l2o_theta_count(l2o_handle h);
+int64_t l2o_state_floats(l2o_handle h); /* per coordinate: 2*sum(H_l) */
+
+int l2o_step(l2o_handle h, const l2o_step_args* a, void* stream);
+int l2o_unroll_fwd(l2o_handle h, const l2o_unroll_args* a, void* stream);
+int l2o_unroll_bwd(l2o_handle h, const l2o_bwd_args* a, void* stream);
+
+/* TF-1.14 Adam on theta: k = 1-based step count. */
+int l2o_adam_step(float* theta, const double* dtheta, float* m, float* v, int64_t n, int32_t k, float lr,
+                  float beta1, float beta2, float eps, void* stream);
+
+/* out [2][n]: row 0 = max(log(|g|+eps)/k, -1), row 1 = clip(g*e^k, -1, 1). */
+int l2o_log_and_sign(const float* g, float* out, int64_t n, float k, void* stream);
+
+/* Number of this library's kernels launched so far in this process (bench.py's gpu_launches). */
+int64_t l2o_launch_count(void);
+const char* l2o_status_string(int status);
+const char* l2o_last_cuda_error(void);
+const char* l2o_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L2O_B200_H_ */

@@ -1,0 +1,141 @@
+"""ctypes binding of ``csrc/libl2o_b200.so`` (C-ABI declared in ``include/l2o_b200.h``).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, this module
+raises.  The product path never routes through ``oracle/`` or plain PyTorch math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libl2o_b200.so")
+INCLUDE = os.path.join(_ROOT, "include")
+
+L2O_OK, L2O_E_INVALID, L2O_E_UNSUPPORTED, L2O_E_CUDA, L2O_E_NOMEM = 0, -1, -2, -3, -4
+PRE_IDENTITY, PRE_LOGSIGN, PRE_FC = 0, 1, 2
+OPT_NONE, OPT_RASTRIGIN_SEP, OPT_QUADRATIC_DIAG = 0, 1, 2
+ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
+
+# every symbol include/l2o_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "l2o_net_create", "l2o_net_destroy", "l2o_net_set_engine", "l2o_theta_count", "l2o_state_floats",
+    "l2o_step", "l2o_unroll_fwd", "l2o_unroll_bwd", "l2o_adam_step", "l2o_log_and_sign",
+    "l2o_launch_count", "l2o_status_string", "l2o_last_cuda_error", "l2o_version",
+]
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("hidden", C.c_int32 * 2), ("preprocess", C.c_int32),
+                ("n_in", C.c_int32), ("fc_dim", C.c_int32), ("logsign_k", C.c_float), ("scale", C.c_float),
+                ("tanh_output", C.c_int32)]
+
+
+_fp = C.c_void_p
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("theta", _fp), ("in0", _fp), ("in1", _fp), ("m", _fp), ("v", _fp),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("p", C.c_float), ("state_in", _fp),
+                ("state_out", _fp), ("x", _fp), ("delta", _fp), ("feat_out", _fp)]
+
+
+class UnrollArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("theta", _fp), ("in_seq", _fp), ("opt_kind", C.c_int32),
+                ("opt_a", _fp), ("opt_b", _fp), ("opt_alpha", C.c_float), ("opt_fscale", C.c_float), ("x", _fp),
+                ("state", _fp), ("ckpt", _fp), ("m", _fp), ("v", _fp), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("step0", C.c_int32), ("g_rec", _fp), ("feat_rec", _fp), ("fx", _fp), ("delta_seq", _fp),
+                ("labels", _fp), ("imit_loss", _fp), ("n_total", C.c_int64)]
+
+
+class BwdArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("theta", _fp), ("in_seq", _fp), ("ckpt", _fp), ("g_rec", _fp),
+                ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp)]
+
+
+class L2OError(RuntimeError):
+    pass
+
+
+def nvcc_command(with_tc: bool = True, out: str = LIB_PATH):
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
+           "-I" + INCLUDE, "-I" + CSRC, "-shared", "-Xcompiler", "-fPIC", "-o", out]
+    if with_tc and os.path.exists(os.path.join(CSRC, "cwlstm_tc.cuh")):
+        cmd.append("-DL2O_WITH_TC")
+    cmd.append(os.path.join(CSRC, "l2o_capi.cu"))
+    return cmd
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(INCLUDE, "l2o_b200.h")]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(p) for p in sources())
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise L2OError("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (fails loudly if it was never built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise L2OError(f"{LIB_PATH} not found - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU/PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.l2o_net_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(NetDesc)]
+    L.l2o_net_create.restype = C.c_int
+    L.l2o_net_destroy.argtypes = [C.c_void_p]
+    L.l2o_net_destroy.restype = None
+    L.l2o_net_set_engine.argtypes = [C.c_void_p, C.c_int32]
+    L.l2o_net_set_engine.restype = C.c_int
+    L.l2o_theta_count.argtypes = [C.c_void_p]
+    L.l2o_theta_count.restype = C.c_int64
+    L.l2o_state_floats.argtypes = [C.c_void_p]
+    L.l2o_state_floats.restype = C.c_int64
+    L.l2o_step.argtypes = [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]
+    L.l2o_step.restype = C.c_int
+    L.l2o_unroll_fwd.argtypes = [C.c_void_p, C.POINTER(UnrollArgs), C.c_void_p]
+    L.l2o_unroll_fwd.restype = C.c_int
+    L.l2o_unroll_bwd.argtypes = [C.c_void_p, C.POINTER(BwdArgs), C.c_void_p]
+    L.l2o_unroll_bwd.restype = C.c_int
+    L.l2o_adam_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_void_p]
+    L.l2o_adam_step.restype = C.c_int
+    L.l2o_log_and_sign.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
+    L.l2o_log_and_sign.restype = C.c_int
+    L.l2o_launch_count.argtypes = []
+    L.l2o_launch_count.restype = C.c_int64
+    for name in ("l2o_status_string", "l2o_last_cuda_error", "l2o_version"):
+        getattr(L, name).restype = C.c_char_p
+    L.l2o_status_string.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != L2O_OK:
+        L = lib()
+        msg = L.l2o_status_string(rc).decode()
+        if rc == L2O_E_CUDA:
+            msg += ": " + L.l2o_last_cuda_error().decode()
+        raise L2OError(f"{what} failed: {msg} ({rc})")

@@ -1,0 +1,153 @@
+"""Thin torch-tensor front end of the C-ABI (``include/l2o_b200.h``).  PyTorch is used only as the
+owner of device memory and streams; all arithmetic happens in the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (BwdArgs, NetDesc, StepArgs, UnrollArgs, L2OError, PRE_FC, PRE_IDENTITY, PRE_LOGSIGN,
+                   OPT_NONE, OPT_QUADRATIC_DIAG, OPT_RASTRIGIN_SEP, ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC)
+
+_PRE = {"identity": PRE_IDENTITY, "LogAndSign": PRE_LOGSIGN, "fc": PRE_FC}
+OPT_KINDS = {"rastrigin_sep": OPT_RASTRIGIN_SEP, "quadratic_diag": OPT_QUADRATIC_DIAG}
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise L2OError(f"{name}: expected a CUDA tensor (this engine has no CPU path)")
+    if t.dtype != dtype:
+        raise L2OError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise L2OError(f"{name}: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class NetHandle:
+    """One optimizer net: shape + run-time scalars (DM/networks.py:157-205)."""
+
+    def __init__(self, layers: Sequence[int] = (20, 20), preprocess_name: str = "identity",
+                 preprocess_options: Optional[dict] = None, scale: float = 1.0, tanh_output: bool = False,
+                 n_in: int = 1):
+        layers = tuple(int(h) for h in layers)
+        if len(layers) > 2:
+            raise L2OError("at most two LSTM layers are supported")
+        if preprocess_name not in _PRE:
+            raise L2OError(f"unsupported preprocess_name {preprocess_name!r}")
+        opts = dict(preprocess_options or {})
+        d = NetDesc()
+        d.n_layers = len(layers)
+        d.hidden[0] = layers[0] if len(layers) > 0 else 0
+        d.hidden[1] = layers[1] if len(layers) > 1 else 0
+        d.preprocess = _PRE[preprocess_name]
+        d.n_in = n_in
+        d.fc_dim = int(opts.get("dim", 0))
+        d.logsign_k = float(opts.get("k", 0.0))
+        d.scale = float(scale)
+        d.tanh_output = 1 if tanh_output else 0
+        self.desc = d
+        self.layers = layers
+        self.n_in = n_in
+        self._h = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.l2o_net_create(C.byref(self._h), C.byref(d)),
+                   f"l2o_net_create(layers={layers}, preprocess={preprocess_name}, n_in={n_in})")
+        self.n_theta = int(L.l2o_theta_count(self._h))
+        self.state_floats = int(L.l2o_state_floats(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().l2o_net_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_engine(self, engine: int):
+        _lib.check(_lib.lib().l2o_net_set_engine(self._h, engine), "l2o_net_set_engine")
+
+    # ---- state arena helpers -------------------------------------------------------------
+    def new_state(self, n: int, device) -> torch.Tensor:
+        return torch.zeros(max(self.state_floats * n, 1), dtype=torch.float32, device=device)
+
+    def state_views(self, arena: torch.Tensor, n: int):
+        """Arena -> tuple over layers of (hidden, cell) views [n, H] (the reference's state structure)."""
+        out, off = [], 0
+        for h in self.layers:
+            hh = arena[off:off + n * h].view(n, h)
+            cc = arena[off + n * h:off + 2 * n * h].view(n, h)
+            out.append((hh, cc))
+            off += 2 * n * h
+        return tuple(out)
+
+    # ---- kernels -------------------------------------------------------------------------
+    def step(self, theta, in0, state_in, state_out, *, in1=None, m=None, v=None, beta1=0.95, beta2=0.95, p=1.0,
+             x=None, delta=None, feat_out=None):
+        a = StepArgs()
+        a.n = in0.numel()
+        a.theta = _ptr(theta, name="theta")
+        a.in0, a.in1 = _ptr(in0, name="in0"), _ptr(in1, name="in1")
+        a.m, a.v = _ptr(m, name="m"), _ptr(v, name="v")
+        a.beta1, a.beta2, a.p = beta1, beta2, p
+        a.state_in, a.state_out = _ptr(state_in, name="state_in"), _ptr(state_out, name="state_out")
+        a.x, a.delta, a.feat_out = _ptr(x, name="x"), _ptr(delta, name="delta"), _ptr(feat_out, name="feat_out")
+        if theta.numel() != self.n_theta:
+            raise L2OError(f"theta has {theta.numel()} elements, net needs {self.n_theta}")
+        _lib.check(_lib.lib().l2o_step(self._h, C.byref(a), _stream()), "l2o_step")
+
+    def unroll_fwd(self, theta, n, T, state, *, in_seq=None, opt_kind=OPT_NONE, opt_a=None, opt_b=None,
+                   opt_alpha=10.0, opt_fscale=1.0, x=None, ckpt=None, m=None, v=None, beta1=0.95, beta2=0.95,
+                   step0=1, g_rec=None, feat_rec=None, fx=None, delta_seq=None, labels=None, imit_loss=None,
+                   n_total=0):
+        a = UnrollArgs()
+        a.n, a.T = n, T
+        a.theta = _ptr(theta, name="theta")
+        a.in_seq = _ptr(in_seq, name="in_seq")
+        a.opt_kind = opt_kind
+        a.opt_a, a.opt_b = _ptr(opt_a, name="opt_a"), _ptr(opt_b, name="opt_b")
+        a.opt_alpha, a.opt_fscale = opt_alpha, opt_fscale
+        a.x, a.state, a.ckpt = _ptr(x, name="x"), _ptr(state, name="state"), _ptr(ckpt, name="ckpt")
+        a.m, a.v = _ptr(m, name="m"), _ptr(v, name="v")
+        a.beta1, a.beta2, a.step0 = beta1, beta2, step0
+        a.g_rec, a.feat_rec = _ptr(g_rec, name="g_rec"), _ptr(feat_rec, name="feat_rec")
+        a.fx = _ptr(fx, torch.float64, "fx")
+        a.delta_seq, a.labels = _ptr(delta_seq, name="delta_seq"), _ptr(labels, name="labels")
+        a.imit_loss = _ptr(imit_loss, torch.float64, "imit_loss")
+        a.n_total = n_total
+        _lib.check(_lib.lib().l2o_unroll_fwd(self._h, C.byref(a), _stream()), "l2o_unroll_fwd")
+
+    def unroll_bwd(self, theta, n, T, in_seq, ckpt, dtheta, *, g_rec=None, labels=None, n_total=0):
+        a = BwdArgs()
+        a.n, a.T = n, T
+        a.theta = _ptr(theta, name="theta")
+        a.in_seq, a.ckpt = _ptr(in_seq, name="in_seq"), _ptr(ckpt, name="ckpt")
+        a.g_rec, a.labels = _ptr(g_rec, name="g_rec"), _ptr(labels, name="labels")
+        a.n_total = n_total
+        a.dtheta = _ptr(dtheta, torch.float64, "dtheta")
+        _lib.check(_lib.lib().l2o_unroll_bwd(self._h, C.byref(a), _stream()), "l2o_unroll_bwd")
+
+
+def adam_step(theta, dtheta, m, v, k: int, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+    """tf.train.AdamOptimizer update of theta in place (DM/meta.py:411-413)."""
+    _lib.check(_lib.lib().l2o_adam_step(_ptr(theta, name="theta"), _ptr(dtheta, torch.float64, "dtheta"),
+                                        _ptr(m, name="m"), _ptr(v, name="v"), theta.numel(), k, lr, beta1, beta2,
+                                        eps, _stream()), "l2o_adam_step")
+
+
+def log_and_sign(g: torch.Tensor, k: float) -> torch.Tensor:
+    """preprocess.LogAndSign on a flat tensor; returns [2, n] (log row, sign row)."""
+    out = torch.empty(2, g.numel(), dtype=torch.float32, device=g.device)
+    _lib.check(_lib.lib().l2o_log_and_sign(_ptr(g, name="g"), _ptr(out), g.numel(), k, _stream()), "l2o_log_and_sign")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().l2o_launch_count())

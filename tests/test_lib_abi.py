@@ -1,0 +1,53 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/l2o_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from open_l2o_b200 import _lib
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "l2o_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(l2o_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared() == sorted(_lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built (run __graft_entry__.build())")
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared():
+        assert hasattr(L, name), name
+    L.l2o_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.l2o_version()
+    L.l2o_status_string.restype = ctypes.c_char_p
+    assert L.l2o_status_string(-2) and L.l2o_launch_count() >= 0
+
+
+def test_net_create_validates_without_gpu():
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    from open_l2o_b200.engine import NetHandle
+    h = NetHandle(layers=(20, 20))
+    assert h.n_theta == 5061 and h.state_floats == 80
+    assert NetHandle(layers=(20, 20), preprocess_name="LogAndSign", preprocess_options={"k": 5}).n_theta == 5141
+    assert NetHandle(layers=(20, 20), preprocess_name="fc", preprocess_options={"dim": 20}, n_in=2).n_theta == 6641
+    with pytest.raises(_lib.L2OError):
+        NetHandle(layers=(33, 5))
+
+
+def test_product_package_never_imports_oracle():
+    root = os.path.dirname(_lib.__file__)
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|import_module\([\"']oracle|oracle[./]l2o_oracle", src, re.M), f
