@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py - coordinate-updates/sec of the learned-optimizer inner loop (BASELINE.json metric).
+
+A "step" is one full ``meta_minimize`` unroll of the hot path: T-step forward unroll (fused, state
+on-chip) + BPTT + d-theta reduction [+ one NCCL all-reduce at N>1] + TF-Adam, through the public
+``MetaOptimizer`` / ``Session.run([fx, update, step])`` surface.  Workload (default): BASELINE config #5,
+L2O-DM (LSTM-20x2, identity preprocess) on separable Rastrigin, 1M coordinates PER GPU (weak scaling),
+unroll T=100.  Synthetic data, random-init weights (seeded).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  torchrun --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...     # the CPU oracle (port of the reference's algorithm) on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FLOP_PER_UPDATE_INFER = {"dm_identity": 9800.0, "dm_logsign": 9960.0, "rnnprop": 12920.0}
+METRIC = "coordinate-updates/sec (N_params x unroll_steps)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rastrigin", choices=["rastrigin", "lasso", "mlp", "rnnprop_mlp", "quadratic"])
+    ap.add_argument("--coords", type=int, default=0, help="coordinates per GPU (0 = workload default)")
+    ap.add_argument("--unroll", type=int, default=0, help="T (0 = workload default)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-coords", type=int, default=4096)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    # name: (description, default coords/GPU, default T, net kind)
+    "rastrigin": ("L2O-DM, separable Rastrigin d=1e6 per GPU, LSTM-20x2 identity, unroll=100 (BASELINE config #5)",
+                  1000000, 100, "dm_identity"),
+    "lasso": ("L2O-DM, Lasso m=250 n=500 batch=128 synthetic, unroll=100 (BASELINE config #2)", 64000, 100,
+              "dm_identity"),
+    "mlp": ("L2O-DM LogAndSign, 1M-coordinate MLP 784-1263-10 synthetic batch 128, unroll=20 (target line)",
+            1004105, 20, "dm_logsign"),
+    "rnnprop_mlp": ("L2O-RNNProp, MLP 784-100-10 synthetic batch 128, unroll=20 (BASELINE config #3)", 79510, 20,
+                    "rnnprop"),
+    "quadratic": ("L2O-DM, quadratic 128x10, unroll=20 (BASELINE config #1)", 1280, 20, "dm_identity"),
+}
+
+
+def make_problem(name, coords, rank):
+    from open_l2o_b200 import problems
+    if name == "rastrigin":
+        return problems.rastrigin_separable(num_dims=coords), {"cw": {"net": "CoordinateWiseDeepLSTM", "net_options": {
+            "layers": (20, 20), "scale": 0.1}}}, "dm"
+    if name == "quadratic":
+        return problems.quadratic(batch_size=128, num_dims=10), {"cw": {"net": "CoordinateWiseDeepLSTM", "net_options": {
+            "layers": (20, 20), "scale": 0.1}}}, "dm"
+    if name == "lasso":
+        g = torch.Generator().manual_seed(2 + rank)
+        A = torch.randn(128, 250, 500, generator=g) / (250 ** 0.5)
+        b = torch.randn(128, 250, 1, generator=g)
+        return problems.lasso_fixed(A, b), {"cw": {"net": "CoordinateWiseDeepLSTM", "net_options": {
+            "layers": (20, 20), "scale": 0.1}}}, "dm"
+    if name == "mlp":
+        from open_l2o_b200 import util
+        return problems.mlp(layers=(1263,)), {"cw": util.get_default_net_config(None)}, "dm"
+    if name == "rnnprop_mlp":
+        return problems.mlp(layers=(100,)), {"rp": {"net": "RNNprop", "net_options": {
+            "layers": (20, 20), "preprocess_name": "fc", "preprocess_options": {"dim": 20}, "scale": 0.01,
+            "tanh_output": True}}}, "rnnprop"
+    raise ValueError(name)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason sampler for the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(workload, T, coords, threads, mode="train"):
+    """Times the oracle (CPU restatement of the reference's algorithm) on a bounded sample of the workload."""
+    from oracle import l2o_oracle as orc   # bench.py's cpu_baseline / --impl reference leg only
+    torch.set_num_threads(threads)
+    spec = orc.NetSpec(layers=(20, 20), scale=0.1)
+    theta = orc.init_theta(spec, seed=0, out_gain=1.0)
+    gen = torch.Generator().manual_seed(1)
+    a, b, x0 = (torch.randn(coords, generator=gen) for _ in range(3))
+    prob = orc.FusedProblem("rastrigin_sep", a, b, 10.0, 1.0 / coords)
+    tr = orc.MetaTrainerOracle(spec, theta, None, lr=0.001, grad_of=prob.f_and_g)
+    tr.reset(x0)
+
+    def one():
+        t0 = time.perf_counter()
+        tr.run_unroll(T, train=(mode == "train"))
+        return time.perf_counter() - t0
+    return one
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (TF-1.14/Sonnet cannot be installed
+    here; the oracle port stands in, kind="port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, dcoords, dT, _ = WORKLOADS["rastrigin"]
+    T = args.unroll or dT
+    threads = os.cpu_count() or 1
+    n = args.cpu_sample_coords
+    one = cpu_oracle_rate("rastrigin", T, n, threads)
+    for _ in range(args.warmup):
+        one()
+    times = [one() for _ in range(args.steps)]
+    tot = sum(times)
+    value = n * T * args.steps / tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "coordinate-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "coords_per_gpu": dcoords, "unroll": T, "mode": "train (fwd+BPTT+Adam)"},
+        "cpu_baseline": {"value": value, "unit": "coordinate-updates/s", "cores": threads, "kind": "port",
+                         "sample": "%d coordinates x T=%d train unroll per step (torch-CPU oracle, autograd BPTT)" % (n, T)},
+        "e2e": {"value": value, "unit": "coordinate-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from open_l2o_b200 import engine as eng, meta
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    desc, dcoords, dT, netkind = WORKLOADS[args.workload]
+    coords = args.coords or dcoords
+    T = args.unroll or dT
+    problem, net_config, flavour = make_problem(args.workload, coords, rank)
+    cls = meta.RNNpropMetaOptimizer if flavour == "rnnprop" else meta.MetaOptimizer
+    optimizer = cls(seed=rank, distributed=distributed, **net_config)
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, "w")      # the reference prints variable lists at graph build; keep stdout = 1 JSON line
+    try:
+        ms = optimizer.meta_minimize(problem, T, learning_rate=0.001)
+    finally:
+        sys.stdout = _stdout
+    prog = optimizer.program
+    coords = prog.N
+    if args.engine != "auto":
+        for net in prog.nets.values():
+            net.handle.set_engine({"ffma": eng.ENGINE_FFMA, "tc": eng.ENGINE_TC}[args.engine])
+    sess = meta.Session()
+    sess.run(ms.reset)
+    fetch = [ms.fx, ms.update, ms.step]
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") -----------------------------------------------------
+    for _ in range(args.warmup):
+        sess.run(fetch)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cost = sess.run(fetch)[0]
+    e1.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    t_dev = e0.elapsed_time(e1) / 1e3
+    sampler.stop_flag = True
+    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_dev = float(tt.item())
+    value = coords * world * T * args.steps / t_dev
+
+    # ---- per-kernel timing of the dominant kernel (BPTT) for the roofline ---------------------------
+    kb0, kb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kf0, kf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r = prog.runs[0]
+    h = r.net.handle
+    roof = None
+    if prog.fused is not None:
+        fw, bw = [], []
+        for _ in range(max(2, min(args.steps, 3))):
+            prog.fx_buf.zero_()
+            xw = prog.X.clone()
+            st = r.state.clone()
+            kf0.record()
+            h.unroll_fwd(r.net.theta, r.n, T, st, opt_kind=eng.OPT_KINDS[prog.fused.kind],
+                         opt_a=prog.const_vals[prog.fused.a], opt_b=prog.const_vals[prog.fused.b],
+                         opt_alpha=prog.fused.alpha, opt_fscale=prog.fused.fscale, x=xw, ckpt=r.ckpt, g_rec=r.g_rec,
+                         fx=prog.fx_buf)
+            kf1.record()
+            dth = torch.zeros_like(prog.dtheta[r.key])
+            kb0.record()
+            h.unroll_bwd(r.net.theta, r.n, T, r.g_rec, r.ckpt, dth, g_rec=r.g_rec)
+            kb1.record()
+            torch.cuda.synchronize()
+            fw.append(kf0.elapsed_time(kf1) / 1e3)
+            bw.append(kb0.elapsed_time(kb1) / 1e3)
+        t_f, t_b = sum(fw) / len(fw), sum(bw) / len(bw)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        fl = FLOP_PER_UPDATE_INFER[netkind]
+        ach_b = 2.0 * fl * r.n * T / t_b / 1e12          # backward = two more GEMMs of the forward's shape
+        ach_f = fl * r.n * T / t_f / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("unroll_bwd_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "unroll_bwd (BPTT)", "achieved": ach_b, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach_b / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF",
+                "fwd_kernel": {"achieved": ach_f, "frac": ach_f / peak, "ms": 1e3 * t_f,
+                               "coord_updates_per_s": r.n * T / t_f},
+                "bwd_ms": 1e3 * t_b,
+                "alg_flop_per_coord_update": {"fwd": fl, "bwd": 2 * fl}}
+
+    # ---- end-to-end through the public API with HOST buffers ------------------------------------
+    e2e = None
+    if prog.fused is not None:
+        f = prog.fused
+        hx = prog.X.cpu().pin_memory()
+        ha = prog.const_vals[f.a].cpu().pin_memory()
+        hb = prog.const_vals[f.b].cpu().pin_memory()
+        hout = torch.empty(coords, dtype=torch.float32).pin_memory()
+        fetch2 = [ms.fx, ms.update, ms.step]
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            prog.X.copy_(hx, non_blocking=True)
+            prog.const_vals[f.a].copy_(ha, non_blocking=True)
+            prog.const_vals[f.b].copy_(hb, non_blocking=True)
+            cost = sess.run(fetch2)[0]                 # float(fx) = device->host read of the loss
+            hout.copy_(prog.X, non_blocking=True)      # updated parameters back to the host
+        g1.record()
+        barrier()
+        t_e = torch.tensor([g0.elapsed_time(g1) / 1e3], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": coords * world * T * args.steps / float(t_e.item()), "unit": "coordinate-updates/s",
+               "h2d_bytes_per_step": 3 * 4 * coords, "d2h_bytes_per_step": 4 * coords + 8}
+    else:
+        e2e = {"value": value, "unit": "coordinate-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+               "note": "external-gradient workload: optimizee tensors are device-resident by construction"}
+
+    # ---- CPU baseline (oracle port on the host cores; rank 0, N=1 only) ----------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_s = args.cpu_sample_coords
+        one = cpu_oracle_rate(args.workload, T, n_s, threads)
+        one()
+        ts = [one() for _ in range(2)]
+        cpu = {"value": n_s * T * len(ts) / sum(ts), "unit": "coordinate-updates/s", "cores": threads, "kind": "port",
+               "sample": "%d coordinates x T=%d separable-Rastrigin train unroll (fwd+autograd BPTT+Adam), torch-CPU "
+                         "oracle, %d timed unrolls after 1 warm-up" % (n_s, T, len(ts))}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "coordinate-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "coords_per_gpu": coords, "unroll": T, "mode": "train (fwd+BPTT+Adam)",
+                       "regime": "fused" if prog.fused is not None else "external-gradient",
+                       "engine": args.engine, "parallelism": "dp%d (coordinates sharded)" % world,
+                       "l2_policy": "working set (checkpoints %.1f GB/GPU) >> 126 MB L2" % (r.ckpt.numel() * 4 / 1e9),
+                       "last_fx": cost},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

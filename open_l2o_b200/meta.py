@@ -1,0 +1,441 @@
+"""Learning-to-learn (meta) optimizer behind the reference's ``MetaOptimizer`` surface (DM/meta.py).
+
+The reference builds a TF graph and crosses the device boundary once per unroll with
+``sess.run([cost, update, step])``.  Here ``meta_loss`` / ``meta_minimize`` return lightweight op
+handles and ``Session.run`` executes one fused unroll (forward T steps [+ BPTT + Adam] + carry-over)
+with the same fetch semantics:
+
+  * all fetches of one ``run`` are evaluated from the same pre-update theta / x / state
+    (TF evaluates ``update`` and ``step`` in the same step as ``cost``);
+  * ``update`` commits x <- x_T, state <- s_T (truncated-BPTT carry-over, DM/meta.py:385-389);
+  * ``step`` applies TF-Adam to the optimizer nets' variables (DM/meta.py:411-413);
+  * ``reset`` re-runs the initializers of state + x + constants (DM/meta.py:378-383).
+
+Two regimes: *fused* (separable optimizee evaluated in-kernel, one launch for all T steps) and
+*external-gradient* (torch autograd between single-step launches, state checkpointed in HBM).
+"""
+from __future__ import annotations
+
+import collections
+import os
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+from . import networks
+from .variables import variable_getter
+
+MetaLoss = collections.namedtuple("MetaLoss", "loss, update, reset, fx, x")
+MetaStep = collections.namedtuple("MetaStep", "step, update, reset, fx, x")
+
+
+class Op(object):
+    """Handle returned in MetaLoss / MetaStep; evaluated by Session.run."""
+
+    def __init__(self, kind, program):
+        self.kind, self.program = kind, program
+
+    def __repr__(self):
+        return "<l2o op {}>".format(self.kind)
+
+
+class Placeholder(object):
+    def __init__(self, name):
+        self.name = name
+
+
+class Session(object):
+    """Minimal stand-in for tf.Session: ``run(fetches, feed_dict)``."""
+
+    def run(self, fetches, feed_dict=None):
+        flat = []
+
+        def walk(f):
+            if isinstance(f, (list, tuple)):
+                for g in f:
+                    walk(g)
+            elif isinstance(f, Op):
+                flat.append(f)
+            elif f is not None:
+                raise TypeError("cannot fetch {!r}".format(f))
+        walk(fetches)
+        results = {}
+        for prog in {id(op.program): op.program for op in flat}.values():
+            kinds = set(op.kind for op in flat if op.program is prog)
+            results[id(prog)] = prog.execute(kinds, feed_dict or {})
+
+        def build(f):
+            if isinstance(f, list):
+                return [build(g) for g in f]
+            if isinstance(f, tuple):
+                return tuple(build(g) for g in f)
+            if f is None:
+                return None
+            return results[id(f.program)].get(f.kind)
+        return build(fetches)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+# ------------------------------------------------------------------------------------------------
+def _get_variables(func, gen, device):
+    """Call ``func`` once, capturing the tensors it creates (DM/meta.py:102-128).
+    Returns (variables, constants): lists of dicts {name, shape, init}."""
+    variables, constants = [], []
+
+    def getter(name, shape, dtype, initializer, trainable):
+        if initializer is None:
+            raise ValueError("variable {!r} needs an initializer".format(name))
+        rec = dict(name=name, shape=shape, init=initializer)
+        (variables if trainable else constants).append(rec)
+        return initializer(shape, gen).to(device=device, dtype=torch.float32)
+
+    with variable_getter(getter), torch.no_grad():
+        func()
+    return variables, constants
+
+
+def _make_nets(variables, config, net_assignments):
+    """DM/meta.py:162-216, same errors."""
+    name_to_index = dict((v["name"], i) for i, v in enumerate(variables))
+    if net_assignments is None:
+        if len(config) != 1:
+            raise ValueError("Default net_assignments can only be used if there is a single net config.")
+        key = next(iter(config))
+        nets = {key: networks.factory(**config[key])}
+        keys, subsets = [key], [list(range(len(variables)))]
+    else:
+        nets, keys, subsets = {}, [], []
+        for key, names in net_assignments:
+            if key in nets:
+                raise ValueError("Repeated netid in net_assigments.")
+            nets[key] = networks.factory(**config[key])
+            subsets.append([name_to_index[name] for name in names])
+            keys.append(key)
+    return nets, keys, subsets
+
+
+class _Run(object):
+    """A maximal contiguous slice of the flat coordinate arena served by one net."""
+
+    def __init__(self, key, net, off, n):
+        self.key, self.net, self.off, self.n = key, net, off, n
+
+
+class _Program(object):
+    """One meta_loss graph: variables, nets, state, workspaces and the unroll executor."""
+
+    def __init__(self, optimizer, make_loss, len_unroll, net_assignments, second_derivatives, learning_rate=None):
+        if second_derivatives:
+            raise NotImplementedError("second_derivatives=True needs optimizee Hessian-vector products "
+                                      "(out of scope, SURVEY.md Appendix B)")
+        if not torch.cuda.is_available():
+            raise _engine.L2OError("MetaOptimizer needs a CUDA device (no CPU path)")
+        self.opt = optimizer
+        self.make_loss = make_loss
+        self.T = int(len_unroll)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.gen = torch.Generator().manual_seed(optimizer.seed)
+        self.learning_rate = learning_rate
+        self.variables, self.constants = _get_variables(make_loss, torch.Generator().manual_seed(optimizer.seed),
+                                                        self.device)
+        print("Optimizee variables")
+        print([v["name"] for v in self.variables])
+        print("Problem variables")
+        print([c["name"] for c in self.constants])
+        self.nets, self.net_keys, self.subsets = _make_nets(self.variables, optimizer._config, net_assignments)
+        optimizer._nets = self.nets
+
+        # flat arena: variables ordered so that each net's subset is contiguous where possible
+        order = []
+        for subset in self.subsets:
+            for j in subset:
+                if j not in order:
+                    order.append(j)
+        for j in range(len(self.variables)):
+            if j not in order:
+                order.append(j)
+        self.var_off, off = {}, 0
+        for j in order:
+            self.var_off[j] = off
+            off += int(np.prod(self.variables[j]["shape"])) if self.variables[j]["shape"] else 1
+        self.N = off
+        self.runs = []
+        for key, subset in zip(self.net_keys, self.subsets):
+            cur = None
+            for j in subset:
+                n = int(np.prod(self.variables[j]["shape"])) if self.variables[j]["shape"] else 1
+                o = self.var_off[j]
+                if cur is not None and cur.off + cur.n == o:
+                    cur.n += n
+                else:
+                    cur = _Run(key, self.nets[key], o, n)
+                    self.runs.append(cur)
+        self.X = torch.zeros(self.N, device=self.device)
+        self.const_vals = {}
+        self.fused = getattr(make_loss, "fused", None) if os.environ.get("L2O_DISABLE_FUSED") != "1" else None
+        if self.fused is not None and not (len(self.runs) == 1 and len(self.variables) == 1 and self.runs[0].n == self.N):
+            self.fused = None
+        self.adam = {k: dict(m=torch.zeros_like(net.theta), v=torch.zeros_like(net.theta), k=0)
+                     for k, net in self.nets.items()}
+        self.dtheta = {k: torch.zeros(net.theta.numel(), dtype=torch.float64, device=self.device)
+                       for k, net in self.nets.items()}
+        self.step_placeholder = Placeholder("step")
+        self.unroll_idx = 0
+        self._alloc_workspaces()
+        self.reset()
+
+    # ---- memory ---------------------------------------------------------------------------------
+    def _alloc_workspaces(self):
+        T = self.T
+        for r in self.runs:
+            sf = r.net.handle.state_floats
+            r.state = r.net.handle.new_state(r.n, self.device)
+            r.ckpt = torch.zeros((T + 1) * max(sf * r.n, 1), device=self.device)
+            r.g_rec = torch.zeros(T + 1, r.n, device=self.device)
+            r.x_work = torch.zeros(r.n, device=self.device)
+            if r.net.handle.n_in == 2:
+                r.m = torch.zeros(r.n, device=self.device)
+                r.v = torch.zeros(r.n, device=self.device)
+                r.m_work, r.v_work = torch.zeros_like(r.m), torch.zeros_like(r.v)
+                r.feat_rec = torch.zeros(T, 2, r.n, device=self.device)
+        self.fx_buf = torch.zeros(T + 1, dtype=torch.float64, device=self.device)
+
+    def reset(self):
+        """variables_initializer(state + x + constants) (DM/meta.py:378-383)."""
+        for v, j in zip(self.variables, range(len(self.variables))):
+            n = int(np.prod(v["shape"])) if v["shape"] else 1
+            o = self.var_off[j]
+            self.X[o:o + n].copy_(v["init"](v["shape"], self.gen).reshape(-1).to(self.device))
+        for c in self.constants:
+            self.const_vals[c["name"]] = c["init"](c["shape"], self.gen).to(self.device, torch.float32).contiguous()
+        for r in self.runs:
+            r.state.zero_()
+            if r.net.handle.n_in == 2:
+                r.m.zero_()
+                r.v.zero_()
+        self.unroll_idx = 0
+
+    # ---- optimizee evaluation --------------------------------------------------------------------
+    def _loss_at(self, Xflat):
+        """_make_with_custom_variables (DM/meta.py:131-155): trainables popped in creation order."""
+        queue = collections.deque(range(len(self.variables)))
+
+        def getter(name, shape, dtype, initializer, trainable):
+            if trainable:
+                j = queue.popleft()
+                n = int(np.prod(shape)) if shape else 1
+                o = self.var_off[j]
+                return Xflat[o:o + n].view(shape)
+            return self.const_vals[name]
+
+        with variable_getter(getter):
+            return self.make_loss()
+
+    def _value_and_grad(self, Xflat):
+        Xl = Xflat.detach().requires_grad_(True)
+        with torch.enable_grad():
+            fx = self._loss_at(Xl)
+            (g,) = torch.autograd.grad(fx, Xl, allow_unused=True)
+        if g is None:
+            g = torch.zeros_like(Xl)
+        return fx.detach(), g.contiguous()
+
+    # ---- the unroll --------------------------------------------------------------------------------
+    def _step0(self, feed):
+        if self.step_placeholder in feed:
+            return int(feed[self.step_placeholder])
+        return self.unroll_idx * self.T + 1
+
+    def _forward_fused(self, train, step0):
+        r, T, f = self.runs[0], self.T, self.fused
+        h = r.net.handle
+        r.x_work.copy_(self.X)
+        state = r.ckpt[:max(h.state_floats * r.n, 1)]
+        work_state = r.state.clone()
+        self.fx_buf.zero_()
+        kw = {}
+        if h.n_in == 2:
+            r.m_work.copy_(r.m)
+            r.v_work.copy_(r.v)
+            kw = dict(m=r.m_work, v=r.v_work, beta1=self.opt.beta1, beta2=self.opt.beta2, step0=step0,
+                      feat_rec=r.feat_rec)
+        h.unroll_fwd(r.net.theta, r.n, T, work_state, opt_kind=_engine.OPT_KINDS[f.kind],
+                     opt_a=self.const_vals[f.a].reshape(-1), opt_b=self.const_vals[f.b].reshape(-1),
+                     opt_alpha=f.alpha, opt_fscale=f.fscale, x=r.x_work, ckpt=r.ckpt if train else None,
+                     g_rec=r.g_rec, fx=self.fx_buf, **kw)
+        del state
+        r.state_final = work_state
+        return self.fx_buf
+
+    def _forward_external(self, train, step0):
+        T = self.T
+        Xw = self.X.clone()
+        fxs = []
+        for r in self.runs:
+            sf = r.net.handle.state_floats
+            r.ckpt[:max(sf * r.n, 1)].copy_(r.state)
+            if r.net.handle.n_in == 2:
+                r.m_work.copy_(r.m)
+                r.v_work.copy_(r.v)
+        for t in range(T):
+            fx, g = self._value_and_grad(Xw)
+            fxs.append(fx)
+            for r in self.runs:
+                h = r.net.handle
+                slot = max(h.state_floats * r.n, 1)
+                r.g_rec[t].copy_(g[r.off:r.off + r.n])
+                kw = {}
+                if h.n_in == 2:
+                    kw = dict(m=r.m_work, v=r.v_work, beta1=self.opt.beta1, beta2=self.opt.beta2,
+                              p=float(step0 + t), feat_out=r.feat_rec[t])
+                h.step(r.net.theta, r.g_rec[t], r.ckpt[t * slot:(t + 1) * slot], r.ckpt[(t + 1) * slot:(t + 2) * slot],
+                       x=Xw[r.off:r.off + r.n], **kw)
+        if train:
+            fx, g = self._value_and_grad(Xw)
+            for r in self.runs:
+                r.g_rec[T].copy_(g[r.off:r.off + r.n])
+        else:
+            with torch.no_grad():
+                fx = self._loss_at(Xw)
+        fxs.append(fx)
+        for r in self.runs:
+            slot = max(r.net.handle.state_floats * r.n, 1)
+            r.state_final = r.ckpt[T * slot:(T + 1) * slot]
+            r.x_work = Xw[r.off:r.off + r.n]
+        self._Xw = Xw
+        return torch.stack([f.reshape(()).double() for f in fxs])
+
+    def execute(self, kinds, feed):
+        if kinds == {"reset"}:
+            self.reset()
+            return {}
+        if "reset" in kinds:
+            raise ValueError("fetch `reset` on its own (the reference runs it separately, DM/util.py:37)")
+        train = "step" in kinds
+        commit = "update" in kinds
+        step0 = self._step0(feed)
+        T = self.T
+        fx = self._forward_fused(train, step0) if self.fused is not None else self._forward_external(train, step0)
+        out = {}
+        if train:
+            for d in self.dtheta.values():
+                d.zero_()
+            for r in self.runs:
+                h = r.net.handle
+                in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
+                h.unroll_bwd(r.net.theta, r.n, T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec)
+            if self.opt.distributed:
+                import torch.distributed as dist
+                packed = torch.cat([self.dtheta[k] for k in self.nets] + [fx])
+                dist.all_reduce(packed)
+                off = 0
+                for k in self.nets:
+                    n = self.dtheta[k].numel()
+                    self.dtheta[k].copy_(packed[off:off + n])
+                    off += n
+                fx = packed[off:]
+        elif self.opt.distributed:
+            import torch.distributed as dist
+            fx = fx.clone()
+            dist.all_reduce(fx)
+        if "loss" in kinds:
+            out["loss"] = float(fx.sum().item())
+        if "fx" in kinds:
+            out["fx"] = float(fx[T].item())
+        if "x" in kinds:
+            xf = self.runs[0].x_work if self.fused is not None else self._Xw
+            out["x"] = [xf[self.var_off[j]:self.var_off[j] + (int(np.prod(v["shape"])) if v["shape"] else 1)]
+                        .reshape(v["shape"]).cpu().numpy() for j, v in enumerate(self.variables)]
+        self.last_fx = fx
+        if train:
+            for k, net in self.nets.items():
+                ad = self.adam[k]
+                ad["k"] += 1
+                _engine.adam_step(net.theta, self.dtheta[k], ad["m"], ad["v"], ad["k"], lr=self.learning_rate)
+            out["step"] = None
+        if commit:
+            if self.fused is not None:
+                self.X.copy_(self.runs[0].x_work)
+            else:
+                self.X.copy_(self._Xw)
+            for r in self.runs:
+                r.state.copy_(r.state_final)
+                if r.net.handle.n_in == 2:
+                    r.m.copy_(r.m_work)
+                    r.v.copy_(r.v_work)
+            self.unroll_idx += 1
+            out["update"] = None
+        return out
+
+
+class MetaOptimizer(object):
+    """Learning to learn (meta) optimizer (DM/meta.py:219-414)."""
+
+    beta1 = 0.95
+    beta2 = 0.95
+
+    def __init__(self, seed=0, distributed=False, **kwargs):
+        self._nets = None
+        self.seed = seed
+        self.distributed = distributed
+        if not kwargs:
+            # default coordinatewise network (DM/meta.py:244-255)
+            self._config = {
+                "coordinatewise": {
+                    "net": "CoordinateWiseDeepLSTM",
+                    "net_options": {
+                        "layers": (20, 20),
+                        "preprocess_name": "LogAndSign",
+                        "preprocess_options": {"k": 5},
+                        "scale": 0.01,
+                    }}}
+        else:
+            self._config = kwargs
+
+    def save(self, sess=None, path=None, index=None):
+        """Save meta-optimizer (DM/meta.py:255-267; ``index`` as in DM/meta_dm_train.py:257-272)."""
+        result = {}
+        for k, net in self._nets.items():
+            if path is None:
+                filename, key = None, k
+            elif index is not None:
+                filename = os.path.join(path, "{}.l2l-{}".format(k, index))
+                key = filename
+            else:
+                filename = os.path.join(path, "{}.l2l".format(k))
+                key = filename
+            result[key] = networks.save(net, sess, filename=filename)
+        return result
+
+    def restore(self, sess, path, index):
+        """DM/meta_dm_train.py:290-302."""
+        for k, net in self._nets.items():
+            with open(os.path.join(path, "{}.l2l-{}".format(k, index)), "rb") as f:
+                net.set_variables(networks._pickle.load(f))
+
+    def meta_loss(self, make_loss, len_unroll, net_assignments=None, second_derivatives=False):
+        """Returns ops computing the meta-loss (DM/meta.py:269-396)."""
+        prog = _Program(self, make_loss, len_unroll, net_assignments, second_derivatives)
+        self.program = prog
+        self.step_placeholder = prog.step_placeholder
+        return MetaLoss(Op("loss", prog), Op("update", prog), Op("reset", prog), Op("fx", prog), Op("x", prog))
+
+    def meta_minimize(self, make_loss, len_unroll, learning_rate=0.01, **kwargs):
+        """Returns ops minimizing the meta-loss with Adam (DM/meta.py:398-414)."""
+        info = self.meta_loss(make_loss, len_unroll, **kwargs)
+        self.program.learning_rate = learning_rate
+        return MetaStep(Op("step", self.program), *info[1:])
+
+
+class RNNpropMetaOptimizer(MetaOptimizer):
+    """DM/meta_rnnprop_train.py / meta_rnnprop_eval.py: per-coordinate Adam moments feed the net."""
+
+    def __init__(self, beta1=0.95, beta2=0.95, **kwargs):
+        super(RNNpropMetaOptimizer, self).__init__(**kwargs)
+        self.beta1, self.beta2 = beta1, beta2
