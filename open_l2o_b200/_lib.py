@@ -61,32 +61,54 @@ class L2OError(RuntimeError):
     pass
 
 
-def nvcc_command(with_tc: bool = True, out: str = LIB_PATH):
-    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-           "-I" + INCLUDE, "-I" + CSRC, "-shared", "-Xcompiler", "-fPIC", "-o", out]
-    if with_tc and os.path.exists(os.path.join(CSRC, "cwlstm_tc.cuh")):
-        cmd.append("-DL2O_WITH_TC")
-    cmd.append(os.path.join(CSRC, "l2o_capi.cu"))
-    return cmd
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
+              "-I" + INCLUDE, "-I" + CSRC, "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(_ROOT, "build", "obj")
+
+
+def translation_units():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + \
            [os.path.join(INCLUDE, "l2o_b200.h")]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(p) for p in sources())
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
-    cmd = nvcc_command()
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise L2OError("nvcc failed:\n" + r.stdout + r.stderr)
+    """Compile every CUDA translation unit in-tree for sm_100a (nvcc cross-compiles without a GPU) and link
+    ``libl2o_b200.so``.  Objects are rebuilt only when a source/header is newer."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    newest_hdr = max(os.path.getmtime(p) for p in sources() if not p.endswith(".cu"))
+    jobs = []
+    for tu in translation_units():
+        obj = os.path.join(OBJ_DIR, os.path.basename(tu)[:-3] + ".o")
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(tu), newest_hdr)
+        jobs.append((tu, obj, stale))
+
+    def compile_one(job):
+        tu, obj, stale = job
+        if not stale:
+            return None
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-c", "-o", obj, tu]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise L2OError("nvcc failed for %s:\n%s%s" % (tu, r.stdout, r.stderr))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        rebuilt = [o for o in ex.map(compile_one, jobs) if o]
+    objs = [j[1] for j in jobs]
+    if rebuilt or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise L2OError("link failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
 
 

@@ -1,0 +1,465 @@
+// tcgen05 engine (sm_100a): the [coords x K] x [K x 4H] gate contraction on the 5th-gen tensor cores.
+//
+// Design (DESIGN.md "tcgen05 engine"):
+//  * CTA = 2 tiles of 128 coordinates (8 epilogue warps, thread == coordinate == TMEM lane) + 1 warp
+//    that allocates TMEM, stages the weights and issues every tcgen05.mma (single elected thread).
+//  * A operand = the coordinate's [features | 1 | h1 | h2] row, kept IN TENSOR MEMORY (TS-mode MMA):
+//    the epilogue thread that produced h' writes it straight into its own TMEM lane with tcgen05.st,
+//    so the recurrent state never touches shared or global memory between unroll steps; the cell
+//    state c stays in registers.
+//  * B operand = gate weights in shared memory, canonical K-major no-swizzle core-matrix layout,
+//    staged ONCE per CTA by a TMA bulk copy (cp.async.bulk) of a pre-arranged image.
+//  * fp32 parity on tf32 tensor cores: error-compensated 3xTF32 -- A = Ah + Al, B = Bh + Bl with
+//    Ah/Bh exactly representable in tf32; D = Ah.Bh + Al.Bh + Ah.Bl accumulated in fp32 in TMEM.
+//    Biases ride along as a constant-1 column of A.
+//  * accumulators come back with tcgen05.ld (gate columns interleaved i,j,f,o per hidden unit so one
+//    x16 load = 4 complete units); sigmoid/tanh/c/h/output-linear/x+=delta are fused in the epilogue.
+#pragma once
+#include "cwlstm_common.cuh"
+
+namespace l2o {
+namespace tc {
+
+constexpr int kTiles = 2;                    // coordinate tiles per CTA
+constexpr int kEpiThreads = 128 * kTiles;
+constexpr int kThreads = kEpiThreads + 32;   // + MMA / alloc warp
+constexpr int kH = 20;
+constexpr int kN = 4 * kH;                   // 80 gate columns
+constexpr int kXC = 8;                       // feature chunk: cols [0, kXC): features, then the constant 1
+constexpr int kColH1 = kXC;                  // A columns of h1
+constexpr int kColH2 = kXC + kH;             // A columns of h2
+constexpr int kACols = kXC + 2 * kH;         // 48
+constexpr int kK1 = 32;                      // layer-1 K range: cols [0, 32)  (4 zero-weight cols of h2)
+constexpr int kK2 = 48;                      // layer-2 K range: cols [0, 48)  (feature rows zero, 1-col = b2)
+constexpr int kTileCols = kN + 2 * kACols;   // D | A_hi | A_lo = 176 TMEM columns per tile
+constexpr int kTmemCols = 512;
+constexpr int kB1Floats = kK1 * kN;          // 2560
+constexpr int kB2Floats = kK2 * kN;          // 3840
+constexpr int kImgFloats = 2 * (kB1Floats + kB2Floats);  // B1h | B1l | B2h | B2l
+constexpr int kImgBytes = kImgFloats * 4;    // 51200
+constexpr uint32_t kSBO = 128;               // bytes between 8-row (N) core-matrix groups
+constexpr uint32_t kLBO = (kN / 8) * 128;    // bytes between 16-byte K chunks
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::tf32, M=128, K=8)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  tc_wait_ld();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = to_tf32(x);
+  lo = x - hi;  // exact in fp32; the tensor core keeps its top 19 bits
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, N, M=128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute SmemDescriptor): addr>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 << 46
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) |
+         (1ull << 46);
+}
+
+// ------------------------------------------------------------------ weight image
+// Image layout per matrix (K rows, kN cols): float index ((k/4)*(kN/8) + n/8)*32 + (n%8)*4 + k%4, where the
+// MMA column n = 4*u + gate (gate 0..3 = i,j,f,o of hidden unit u) -- one tcgen05.ld x16 = 4 whole units.
+__device__ __forceinline__ int img_index(int k, int n) { return ((k >> 2) * (kN / 8) + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3); }
+
+template <class C>
+__global__ void prep_weights_kernel(const float* __restrict__ theta, float* __restrict__ img) {
+  static_assert(C::H1 == kH && C::H2 == kH && C::F <= 3 && !C::FC, "tc engine: LSTM-20x2, F <= 3");
+  float* b1h = img;
+  float* b1l = img + kB1Floats;
+  float* b2h = img + 2 * kB1Floats;
+  float* b2l = img + 2 * kB1Floats + kB2Floats;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < (kK1 + kK2) * kN; e += gridDim.x * blockDim.x) {
+    const bool l2 = e >= kK1 * kN;
+    const int ee = l2 ? e - kK1 * kN : e;
+    const int k = ee / kN, n = ee % kN;
+    const int u = n >> 2, g = n & 3;
+    const int col = g * kH + u;  // reference gate-column order i|j|f|o blocks (snt.LSTM split)
+    float w = 0.f;
+    if (!l2) {
+      if (k < C::F) w = theta[C::O_W1 + k * C::G1 + col];
+      else if (k == C::F) w = theta[C::O_B1 + col];
+      else if (k >= kColH1 && k < kColH1 + kH) w = theta[C::O_W1 + (C::F + k - kColH1) * C::G1 + col];
+    } else {
+      if (k == C::F) w = theta[C::O_B2 + col];
+      else if (k >= kColH1 && k < kColH1 + 2 * kH) w = theta[C::O_W2 + (k - kColH1) * C::G2 + col];
+    }
+    float hi, lo;
+    split_tf32(w, hi, lo);
+    const int idx = img_index(k, n);
+    (l2 ? b2h : b1h)[idx] = hi;
+    (l2 ? b2l : b1l)[idx] = to_tf32(lo);
+  }
+}
+
+// ------------------------------------------------------------------ epilogue helpers
+// LSTM pointwise update of 4 hidden units from 16 accumulator columns (i,j,f,o interleaved).
+__device__ __forceinline__ void lstm_units4(const float* z, float* c, float* h) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float i = sigmoid_acc(z[4 * u + 0]);
+    const float j = tanh_acc(z[4 * u + 1]);
+    const float f = sigmoid_acc(z[4 * u + 2] + 1.0f);
+    const float o = sigmoid_acc(z[4 * u + 3]);
+    const float cn = fmaf(f, c[u], i * j);
+    c[u] = cn;
+    h[u] = tanh_acc(cn) * o;
+  }
+}
+
+// write 4 values (hi/lo split) to A_hi / A_lo columns [col, col+4)
+__device__ __forceinline__ void st_split4(uint32_t a_hi, uint32_t a_lo, int col, const float* v) {
+  float h0, h1, h2, h3, l0, l1, l2, l3;
+  split_tf32(v[0], h0, l0);
+  split_tf32(v[1], h1, l1);
+  split_tf32(v[2], h2, l2);
+  split_tf32(v[3], h3, l3);
+  tmem_st4(a_hi + col, h0, h1, h2, h3);
+  tmem_st4(a_lo + col, l0, l1, l2, l3);
+}
+
+struct Smem {
+  float img[kImgFloats];          // must stay first (16B-aligned TMA destination, descriptor base)
+  float wo[kH + 4];               // linear/w, linear/b
+  uint64_t wbar;
+  uint64_t a_ready[kTiles];
+  uint64_t d_ready[kTiles];
+  uint32_t tmem_slot;
+  uint32_t pad;
+  double fx[1];                   // [T+1], dynamic tail
+};
+
+template <class C>
+__global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args a, NetRt rt, const float* __restrict__ img) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T;
+  const int64_t n = a.n;
+  const int64_t npairs = (n + kEpiThreads - 1) / kEpiThreads;
+  const bool in_kernel_opt = a.opt_kind != L2O_OPT_NONE;
+  const bool want_fx = in_kernel_opt && a.fx != nullptr;
+
+  if (want_fx)
+    for (int t = threadIdx.x; t <= T; t += blockDim.x) S.fx[t] = 0.0;
+  if (threadIdx.x < kH) S.wo[threadIdx.x] = a.theta[C::O_WO + threadIdx.x];
+  if (threadIdx.x == kH) S.wo[kH] = a.theta[C::O_BO];
+  if (warp == kEpiThreads / 32) {
+    if (lane == 0) {
+      mbar_init(&S.wbar, 1);
+#pragma unroll
+      for (int k = 0; k < kTiles; ++k) {
+        mbar_init(&S.a_ready[k], 128);
+        mbar_init(&S.d_ready[k], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&S.tmem_slot, kTmemCols);
+    tmem_relinquish();
+    if (lane == 0) {
+      mbar_expect_tx(&S.wbar, kImgBytes);
+      tma_bulk_g2s(S.img, img, kImgBytes, &S.wbar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_slot;
+
+  if (warp < kEpiThreads / 32) {
+    // =============================== epilogue warps: thread == coordinate ===============================
+    const int tile = warp >> 2;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t t_d = tmem_base + lane_off + tile * kTileCols;
+    const uint32_t t_ah = t_d + kN;
+    const uint32_t t_al = t_ah + kACols;
+    uint32_t pd = 0;  // d_ready parity
+    const int64_t slot = n * C::SF;
+    double imit = 0.0;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int64_t i = pair * kEpiThreads + tile * 128 + (warp & 3) * 32 + lane;
+      const bool act = i < n;
+      float c1[kH], c2[kH];
+      float x = 0.f, oa = 0.f, ob = 0.f;
+      {
+        float h1[kH], h2[kH];
+#pragma unroll
+        for (int k = 0; k < kH; ++k) { h1[k] = 0.f; h2[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
+        if (act) {
+          load_vec<kH>(a.state + i * kH, h1);
+          load_vec<kH>(a.state + (n + i) * kH, c1);
+          load_vec<kH>(a.state + 2 * n * kH + i * kH, h2);
+          load_vec<kH>(a.state + 2 * n * kH + (n + i) * kH, c2);
+          if (a.ckpt) {
+            store_vec<kH>(a.ckpt + i * kH, h1);
+            store_vec<kH>(a.ckpt + (n + i) * kH, c1);
+            store_vec<kH>(a.ckpt + 2 * n * kH + i * kH, h2);
+            store_vec<kH>(a.ckpt + 2 * n * kH + (n + i) * kH, c2);
+          }
+          if (a.x) x = a.x[i];
+          if (in_kernel_opt) { oa = a.opt_a[i]; ob = a.opt_b[i]; }
+        }
+#pragma unroll
+        for (int q = 0; q < kH / 4; ++q) {
+          st_split4(t_ah, t_al, kColH1 + 4 * q, h1 + 4 * q);
+          st_split4(t_ah, t_al, kColH2 + 4 * q, h2 + 4 * q);
+        }
+      }
+      for (int t = 0; t < T; ++t) {
+        // ---- gradient + preprocessing -> feature chunk of A -------------------------------------
+        float fval = 0.f, raw0 = 0.f;
+        if (act) {
+          if (in_kernel_opt) {
+            optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, raw0);
+            if (a.g_rec) a.g_rec[(int64_t)t * n + i] = raw0;
+          } else {
+            raw0 = a.in_seq[(int64_t)t * n + i];
+          }
+        }
+        {
+          float u[4] = {0.f, 0.f, 0.f, 0.f};
+          float dummy[C::F];
+          preprocess<C>(nullptr, rt, raw0, 0.f, dummy);
+#pragma unroll
+          for (int k = 0; k < C::F; ++k) u[k] = dummy[k];
+          u[C::F] = 1.0f;  // bias column
+          st_split4(t_ah, t_al, 0, u);
+          tmem_st4(t_ah + 4, 0.f, 0.f, 0.f, 0.f);
+          tmem_st4(t_al + 4, 0.f, 0.f, 0.f, 0.f);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&S.a_ready[tile]);
+        if (want_fx) {
+          const double ws = warp_sum_d((double)fval);
+          if (lane == 0) atomicAdd(&S.fx[t], ws);
+        }
+        // ---- layer 1 epilogue ---------------------------------------------------------------
+        mbar_wait(&S.d_ready[tile], pd);
+        pd ^= 1;
+        tc_fence_after();
+        float hrow[kH];
+#pragma unroll
+        for (int q = 0; q < kH / 4; ++q) {
+          float z[16];
+          tmem_ld16(t_d + 16 * q, z);
+          lstm_units4(z, c1 + 4 * q, hrow + 4 * q);
+          st_split4(t_ah, t_al, kColH1 + 4 * q, hrow + 4 * q);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&S.a_ready[tile]);
+        if (act) {
+          if (a.ckpt) {
+            float* ck = a.ckpt + (int64_t)(t + 1) * slot;
+            store_vec<kH>(ck + i * kH, hrow);
+            store_vec<kH>(ck + (n + i) * kH, c1);
+          }
+          if (t == T - 1) store_vec<kH>(a.state + i * kH, hrow);  // final hidden state of layer 1
+        }
+        // ---- layer 2 epilogue + output linear + parameter add ---------------------------------
+        mbar_wait(&S.d_ready[tile], pd);
+        pd ^= 1;
+        tc_fence_after();
+        float y = S.wo[kH];
+#pragma unroll
+        for (int q = 0; q < kH / 4; ++q) {
+          float z[16];
+          tmem_ld16(t_d + 16 * q, z);
+          lstm_units4(z, c2 + 4 * q, hrow + 4 * q);
+          st_split4(t_ah, t_al, kColH2 + 4 * q, hrow + 4 * q);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) y = fmaf(hrow[4 * q + k], S.wo[4 * q + k], y);
+        }
+        const float d = rt.tanh_output ? tanh_acc(y) * rt.scale : y * rt.scale;
+        x += d;
+        if (act) {
+          if (a.ckpt) {
+            float* ck = a.ckpt + (int64_t)(t + 1) * slot + 2 * n * kH;
+            store_vec<kH>(ck + i * kH, hrow);
+            store_vec<kH>(ck + (n + i) * kH, c2);
+          }
+          if (a.delta_seq) a.delta_seq[(int64_t)t * n + i] = d;
+          if (a.labels) {
+            const float r = a.labels[(int64_t)t * n + i] - d;
+            imit += 0.5 * (double)r * (double)r;
+          }
+          if (t == T - 1) store_vec<kH>(a.state + 2 * n * kH + i * kH, hrow);  // final hidden state of layer 2
+        }
+      }
+      // ---- tile epilogue: final cell state / x / f(x_T), g_T ------------------------------------
+      {
+        float fval = 0.f;
+        if (act) {
+          if (in_kernel_opt) {
+            float gT;
+            optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, gT);
+            if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gT;
+          }
+          if (T > 0) {
+            store_vec<kH>(a.state + (n + i) * kH, c1);
+            store_vec<kH>(a.state + 2 * n * kH + (n + i) * kH, c2);
+          }
+          if (a.x) a.x[i] = x;
+        }
+        if (want_fx) {
+          const double ws = warp_sum_d((double)fval);
+          if (lane == 0) atomicAdd(&S.fx[T], ws);
+        }
+      }
+    }
+    if (a.labels && a.imit_loss) {
+      const double ws = warp_sum_d(imit);
+      if (lane == 0) atomicAdd(a.imit_loss, ws / (double)a.n_total);
+    }
+  } else {
+    // =============================== MMA issuer warp ===============================
+    mbar_wait(&S.wbar, 0);  // weights landed (TMA complete_tx)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kN);
+      const uint32_t img_s = smem_u32(S.img);
+      const uint64_t b1h = make_bdesc(img_s);
+      const uint64_t b1l = make_bdesc(img_s + kB1Floats * 4);
+      const uint64_t b2h = make_bdesc(img_s + 2 * kB1Floats * 4);
+      const uint64_t b2l = make_bdesc(img_s + (2 * kB1Floats + kB2Floats) * 4);
+      constexpr uint64_t kStep = (2 * kLBO) >> 4;  // descriptor start-address increment per K=8 chunk
+      uint32_t pa[kTiles] = {0, 0};
+      for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        for (int t = 0; t < T; ++t) {
+#pragma unroll
+          for (int layer = 0; layer < 2; ++layer) {
+#pragma unroll
+            for (int tile = 0; tile < kTiles; ++tile) {
+              const uint32_t t_d = tmem_base + tile * kTileCols;
+              const uint32_t t_ah = t_d + kN;
+              const uint32_t t_al = t_ah + kACols;
+              mbar_wait(&S.a_ready[tile], pa[tile]);
+              pa[tile] ^= 1;
+              tc_fence_after();
+              const int nchunks = (layer == 0 ? kK1 : kK2) / 8;
+              const uint64_t bh = layer == 0 ? b1h : b2h;
+              const uint64_t bl = layer == 0 ? b1l : b2l;
+              for (int kc = 0; kc < nchunks; ++kc) {
+                mma_tf32_ts(t_d, t_al + 8 * kc, bh + kc * kStep, idesc, kc > 0 ? 1u : 0u);
+                mma_tf32_ts(t_d, t_ah + 8 * kc, bl + kc * kStep, idesc, 1u);
+                mma_tf32_ts(t_d, t_ah + 8 * kc, bh + kc * kStep, idesc, 1u);
+              }
+              tc_commit(&S.d_ready[tile]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (want_fx)
+    for (int t = threadIdx.x; t <= T; t += blockDim.x) atomicAdd(&a.fx[t], S.fx[t]);
+  if (warp == kEpiThreads / 32) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------ host side (called from l2o_capi.cu)
+template <class C>
+int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms) {
+  tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img);
+  auto k = tc::unroll_fwd_kernel<C>;
+  const size_t smem = sizeof(tc::Smem) + (size_t)(a.T + 1) * sizeof(double) + 128;
+  if (smem > 220 * 1024) return L2O_E_INVALID;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
+  const int64_t npairs = (a.n + tc::kEpiThreads - 1) / tc::kEpiThreads;
+  const int grid = (int)(npairs < sms ? npairs : sms);
+  k<<<grid, tc::kThreads, smem, st>>>(a, rt, img);
+  return cudaGetLastError() == cudaSuccess ? L2O_OK : L2O_E_CUDA;
+}
+
+}  // namespace l2o

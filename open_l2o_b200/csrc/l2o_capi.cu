@@ -1,42 +1,16 @@
-// C-ABI of the engine (include/l2o_b200.h): argument validation, config dispatch, launches.
+// C-ABI of the engine (include/l2o_b200.h): argument validation and engine dispatch.
 #include <cuda_runtime.h>
 
 #include <atomic>
 #include <cmath>
 #include <cstdio>
-#include <cstring>
 #include <new>
 
-#include "cwlstm_ffma.cuh"
-#include "l2o_b200.h"
-#ifdef L2O_WITH_TC
-#include "cwlstm_tc.cuh"
-#endif
+#include "l2o_internal.h"
 
 namespace {
-
 std::atomic<int64_t> g_launches{0};
 thread_local char g_cuda_err[256] = "";
-
-int cuda_fail(cudaError_t e, const char* where) {
-  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
-  return L2O_E_CUDA;
-}
-#define CUDA_TRY(expr)                                      \
-  do {                                                      \
-    cudaError_t e__ = (expr);                               \
-    if (e__ != cudaSuccess) return cuda_fail(e__, #expr);   \
-  } while (0)
-
-// Net shapes compiled into this build.  (id, PRE, NIN, F, H1, H2)
-#define L2O_FOR_EACH_CFG(X)               \
-  X(0, L2O_PRE_IDENTITY, 1, 1, 20, 20)    \
-  X(1, L2O_PRE_LOGSIGN, 1, 2, 20, 20)     \
-  X(2, L2O_PRE_FC, 2, 20, 20, 20)         \
-  X(3, L2O_PRE_IDENTITY, 1, 1, 0, 0)      \
-  X(4, L2O_PRE_IDENTITY, 1, 1, 1, 0)      \
-  X(5, L2O_PRE_IDENTITY, 1, 1, 1, 1)      \
-  X(6, L2O_PRE_IDENTITY, 1, 1, 2, 3)
 
 int find_cfg(const l2o_net_desc& d) {
   const int h1 = d.n_layers >= 1 ? d.hidden[0] : 0;
@@ -47,93 +21,6 @@ int find_cfg(const l2o_net_desc& d) {
   L2O_FOR_EACH_CFG(X)
 #undef X
   return -1;
-}
-
-struct DevInfo {
-  int sms = 0;
-  bool ok = false;
-};
-DevInfo& dev_info() {
-  static thread_local DevInfo di;
-  static thread_local int cached_dev = -1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess && (dev != cached_dev || !di.ok)) {
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) {
-      di.sms = p.multiProcessorCount;
-      di.ok = true;
-      cached_dev = dev;
-    }
-  }
-  return di;
-}
-
-template <class K>
-int launch_cfg(K kernel, size_t smem, int64_t n, int& grid) {
-  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, l2o::kTile, smem));
-  if (occ < 1) return L2O_E_UNSUPPORTED;
-  DevInfo& di = dev_info();
-  if (!di.ok) return L2O_E_CUDA;
-  const int64_t tiles = (n + l2o::kTile - 1) / l2o::kTile;
-  const int64_t cap = (int64_t)di.sms * occ;
-  grid = (int)(tiles < cap ? tiles : cap);
-  if (grid < 1) grid = 1;
-  return L2O_OK;
-}
-
-}  // namespace
-
-struct l2o_net {
-  l2o_net_desc desc;
-  int cfg;
-  int engine;
-  int64_t n_theta;
-  int64_t state_floats;
-  l2o::NetRt rt;
-};
-
-namespace {
-
-template <class C>
-int do_step(const l2o_net* h, const l2o_step_args& a, cudaStream_t st) {
-  auto k = l2o::step_kernel<C>;
-  const size_t smem = (size_t)(l2o::round4(C::P) + 4) * sizeof(float);
-  int grid = 1;
-  int rc = launch_cfg(k, smem, a.n, grid);
-  if (rc) return rc;
-  k<<<grid, l2o::kTile, smem, st>>>(a, h->rt);
-  g_launches++;
-  CUDA_TRY(cudaGetLastError());
-  return L2O_OK;
-}
-
-template <class C>
-int do_unroll_fwd(const l2o_net* h, const l2o_unroll_args& a, cudaStream_t st) {
-  auto k = l2o::unroll_fwd_kernel<C>;
-  const size_t smem = (size_t)(l2o::round4(C::P) + 4) * sizeof(float) + (size_t)(a.T + 1) * sizeof(double);
-  if (smem > 200 * 1024) return L2O_E_INVALID;
-  int grid = 1;
-  int rc = launch_cfg(k, smem, a.n, grid);
-  if (rc) return rc;
-  k<<<grid, l2o::kTile, smem, st>>>(a, h->rt);
-  g_launches++;
-  CUDA_TRY(cudaGetLastError());
-  return L2O_OK;
-}
-
-template <class C>
-int do_unroll_bwd(const l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {
-  auto k = l2o::unroll_bwd_kernel<C>;
-  const size_t smem = l2o::BwdGeom<C>::BYTES;
-  int grid = 1;
-  int rc = launch_cfg(k, smem, a.n, grid);
-  if (rc) return rc;
-  k<<<grid, l2o::kTile, smem, st>>>(a, h->rt);
-  g_launches++;
-  CUDA_TRY(cudaGetLastError());
-  return L2O_OK;
 }
 
 __global__ void adam_kernel(float* __restrict__ theta, const double* __restrict__ dtheta, float* __restrict__ m,
@@ -156,8 +43,27 @@ __global__ void log_and_sign_kernel(const float* __restrict__ g, float* __restri
   out[i] = lo;
   out[n + i] = sg;
 }
-
 }  // namespace
+
+namespace l2o {
+int set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return L2O_E_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+int device_sms() {
+  static thread_local int cached_dev = -1, sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    sms = v;
+    cached_dev = dev;
+  }
+  return sms;
+}
+}  // namespace l2o
 
 extern "C" {
 
@@ -171,6 +77,8 @@ int l2o_net_create(l2o_handle* out, const l2o_net_desc* d) {
   h->desc = *d;
   h->cfg = cfg;
   h->engine = L2O_ENGINE_AUTO;
+  h->tc_img = nullptr;
+  h->tc_img_dev = -1;
   h->rt.scale = d->scale;
   h->rt.logsign_k = d->logsign_k;
   h->rt.logsign_ek = (float)std::exp((double)d->logsign_k);
@@ -186,15 +94,15 @@ int l2o_net_create(l2o_handle* out, const l2o_net_desc* d) {
   return L2O_OK;
 }
 
-void l2o_net_destroy(l2o_handle h) { delete h; }
+void l2o_net_destroy(l2o_handle h) {
+  if (!h) return;
+  if (h->tc_img) cudaFree(h->tc_img);
+  delete h;
+}
 
 int l2o_net_set_engine(l2o_handle h, int32_t engine) {
   if (!h || engine < L2O_ENGINE_AUTO || engine > L2O_ENGINE_TC) return L2O_E_INVALID;
-#ifndef L2O_WITH_TC
-  if (engine == L2O_ENGINE_TC) return L2O_E_UNSUPPORTED;
-#else
   if (engine == L2O_ENGINE_TC && !l2o::tc_supported(h->cfg)) return L2O_E_UNSUPPORTED;
-#endif
   h->engine = engine;
   return L2O_OK;
 }
@@ -207,20 +115,16 @@ int l2o_step(l2o_handle h, const l2o_step_args* a, void* stream) {
   if (h->state_floats > 0 && (!a->state_in || !a->state_out)) return L2O_E_INVALID;
   if (h->desc.n_in == 2 && !a->m && !a->in1) return L2O_E_INVALID;
   if ((a->m == nullptr) != (a->v == nullptr)) return L2O_E_INVALID;
+  if (a->m && h->desc.n_in != 2) return L2O_E_INVALID;
   if (a->n == 0) return L2O_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-#define X(id, PRE, NIN, F, H1, H2) \
-  if (h->cfg == id) return do_step<l2o::Cfg<PRE, NIN, F, H1, H2>>(h, *a, st);
-  L2O_FOR_EACH_CFG(X)
-#undef X
-  return L2O_E_UNSUPPORTED;
+  return l2o::ffma_step(h, *a, (cudaStream_t)stream);
 }
 
 int l2o_unroll_fwd(l2o_handle h, const l2o_unroll_args* a, void* stream) {
   if (!h || !a || a->n < 0 || a->T < 0 || !a->theta) return L2O_E_INVALID;
   if (a->opt_kind == L2O_OPT_NONE && !a->in_seq && a->T > 0) return L2O_E_INVALID;
-  if (a->opt_kind != L2O_OPT_NONE && (!a->x || !a->opt_a || !a->opt_b)) return L2O_E_INVALID;
   if (a->opt_kind < L2O_OPT_NONE || a->opt_kind > L2O_OPT_QUADRATIC_DIAG) return L2O_E_INVALID;
+  if (a->opt_kind != L2O_OPT_NONE && (!a->x || !a->opt_a || !a->opt_b)) return L2O_E_INVALID;
   if (a->opt_kind != L2O_OPT_NONE && h->desc.n_in == 2 && !a->m) return L2O_E_INVALID;
   if (h->state_floats > 0 && !a->state) return L2O_E_INVALID;
   if ((a->m == nullptr) != (a->v == nullptr)) return L2O_E_INVALID;
@@ -228,18 +132,10 @@ int l2o_unroll_fwd(l2o_handle h, const l2o_unroll_args* a, void* stream) {
   if (a->labels && (!a->imit_loss || a->n_total <= 0)) return L2O_E_INVALID;
   if (a->n == 0) return L2O_OK;
   cudaStream_t st = (cudaStream_t)stream;
-#ifdef L2O_WITH_TC
-  if (h->engine == L2O_ENGINE_TC || (h->engine == L2O_ENGINE_AUTO && l2o::tc_supported(h->cfg) && l2o::tc_fwd_ok(*a))) {
-    int rc = l2o::tc_unroll_fwd(h->cfg, h->rt, *a, st);
-    if (rc == L2O_OK) g_launches++;
-    if (rc != L2O_E_UNSUPPORTED || h->engine == L2O_ENGINE_TC) return rc;
-  }
-#endif
-#define X(id, PRE, NIN, F, H1, H2) \
-  if (h->cfg == id) return do_unroll_fwd<l2o::Cfg<PRE, NIN, F, H1, H2>>(h, *a, st);
-  L2O_FOR_EACH_CFG(X)
-#undef X
-  return L2O_E_UNSUPPORTED;
+  const bool tc_can = l2o::tc_supported(h->cfg) && l2o::tc_fwd_ok(*a);
+  if (h->engine == L2O_ENGINE_TC) return tc_can ? l2o::tc_unroll_fwd(h, *a, st) : L2O_E_UNSUPPORTED;
+  if (h->engine == L2O_ENGINE_AUTO && tc_can && l2o::tc_auto_default()) return l2o::tc_unroll_fwd(h, *a, st);
+  return l2o::ffma_unroll_fwd(h, *a, st);
 }
 
 int l2o_unroll_bwd(l2o_handle h, const l2o_bwd_args* a, void* stream) {
@@ -248,12 +144,7 @@ int l2o_unroll_bwd(l2o_handle h, const l2o_bwd_args* a, void* stream) {
   if (h->state_floats > 0 && !a->ckpt) return L2O_E_INVALID;
   if (!a->g_rec && (!a->labels || a->n_total <= 0)) return L2O_E_INVALID;
   if (a->n == 0 || a->T == 0) return L2O_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-#define X(id, PRE, NIN, F, H1, H2) \
-  if (h->cfg == id) return do_unroll_bwd<l2o::Cfg<PRE, NIN, F, H1, H2>>(h, *a, st);
-  L2O_FOR_EACH_CFG(X)
-#undef X
-  return L2O_E_UNSUPPORTED;
+  return l2o::ffma_unroll_bwd(h, *a, (cudaStream_t)stream);
 }
 
 int l2o_adam_step(float* theta, const double* dtheta, float* m, float* v, int64_t n, int32_t k, float lr, float beta1,
@@ -265,8 +156,8 @@ int l2o_adam_step(float* theta, const double* dtheta, float* m, float* v, int64_
   const int block = 256;
   adam_kernel<<<(int)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(theta, dtheta, m, v, n, (float)lr_t,
                                                                                  beta1, beta2, eps);
-  g_launches++;
-  CUDA_TRY(cudaGetLastError());
+  l2o::count_launch();
+  L2O_CUDA_TRY(cudaGetLastError());
   return L2O_OK;
 }
 
@@ -276,8 +167,8 @@ int l2o_log_and_sign(const float* g, float* out, int64_t n, float k, void* strea
   const int block = 256;
   log_and_sign_kernel<<<(int)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(g, out, n, k,
                                                                                          (float)std::exp((double)k));
-  g_launches++;
-  CUDA_TRY(cudaGetLastError());
+  l2o::count_launch();
+  L2O_CUDA_TRY(cudaGetLastError());
   return L2O_OK;
 }
 
@@ -295,6 +186,6 @@ const char* l2o_status_string(int s) {
 }
 
 const char* l2o_last_cuda_error(void) { return g_cuda_err; }
-const char* l2o_version(void) { return "l2o_b200 0.1 (sm_100a)"; }
+const char* l2o_version(void) { return "l2o_b200 0.2 (sm_100a; engines: ffma, tcgen05)"; }
 
 }  // extern "C"

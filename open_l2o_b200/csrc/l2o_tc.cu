@@ -1,0 +1,30 @@
+// tcgen05 engine translation unit.
+#include "cwlstm_ffma.cuh"   // load_vec / store_vec / preprocess helpers
+#include "cwlstm_tc.cuh"
+#include "l2o_internal.h"
+
+namespace l2o {
+bool tc_supported(int cfg) { return cfg == 0 || cfg == 1; }  // LSTM-20x2 with identity / LogAndSign preprocessing
+bool tc_fwd_ok(const l2o_unroll_args& a) { return a.m == nullptr && a.feat_rec == nullptr; }
+bool tc_auto_default() { return false; }  // flipped to true once the engine is parity-green on the B200
+
+int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st) {
+  if (!tc_supported(h->cfg) || !tc_fwd_ok(a)) return L2O_E_UNSUPPORTED;
+  int dev = 0;
+  L2O_CUDA_TRY(cudaGetDevice(&dev));
+  if (h->tc_img == nullptr || h->tc_img_dev != dev) {
+    if (h->tc_img) cudaFree(h->tc_img);
+    h->tc_img = nullptr;
+    L2O_CUDA_TRY(cudaMalloc(&h->tc_img, tc::kImgBytes));
+    h->tc_img_dev = dev;
+  }
+  const int sms = device_sms();
+  if (sms <= 0) return L2O_E_CUDA;
+  int rc = L2O_E_UNSUPPORTED;
+  if (h->cfg == 0) rc = tc_launch_fwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+  if (h->cfg == 1) rc = tc_launch_fwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+  if (rc == L2O_OK) count_launch(2);
+  if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_unroll_fwd launch");
+  return rc;
+}
+}  // namespace l2o

@@ -310,9 +310,15 @@ def imitation_loss(spec: NetSpec, theta, inputs, labels, state0):
 
 
 def tf_adam_step(theta, grad, m, v, k: int, lr=0.01, b1=0.9, b2=0.999, eps=1e-8):
-    """tf.train.AdamOptimizer (TF 1.14): lr_t = lr*sqrt(1-b2^k)/(1-b1^k); theta -= lr_t*m/(sqrt(v)+eps)."""
-    m = b1 * m + (1 - b1) * grad
-    v = b2 * v + (1 - b2) * grad * grad
+    """tf.train.AdamOptimizer (TF 1.14 ApplyAdam): lr_t = lr*sqrt(1-b2^k)/(1-b1^k);
+    m += (g-m)(1-b1); v += (g^2-v)(1-b2); theta -= lr_t*m/(sqrt(v)+eps).  The hyper-parameters are fp32
+    scalars in TF, so (1-b) is formed in the tensors' dtype (1 - fp32(0.999) != 0.001)."""
+    dt = theta.dtype
+    one = torch.ones((), dtype=dt)
+    omb1 = one - torch.tensor(b1, dtype=dt)
+    omb2 = one - torch.tensor(b2, dtype=dt)
+    m = torch.tensor(b1, dtype=dt) * m + omb1 * grad
+    v = torch.tensor(b2, dtype=dt) * v + omb2 * grad * grad
     lr_t = lr * math.sqrt(1 - b2 ** k) / (1 - b1 ** k)
     theta = theta - lr_t * m / (torch.sqrt(v) + eps)
     return theta, m, v

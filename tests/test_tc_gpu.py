@@ -1,0 +1,87 @@
+"""tcgen05 engine parity: 3xTF32 tensor-core unroll vs the CPU oracle and vs the exact-fp32 FFMA engine."""
+import pytest
+import torch
+
+from oracle import l2o_oracle as orc
+from tests.helpers import REL_TOL, SPECS, arena_to_state, make_handle, rel_err
+from tests.test_kernels_gpu import _fused_problem, _run_prerecorded, _theta
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("name", ["dm_identity", "dm_logsign"])
+@pytest.mark.parametrize("n,T", [(777, 20), (256, 1), (5000, 3)])
+def test_tc_unroll_fwd_prerecorded(name, n, T):
+    from open_l2o_b200.engine import ENGINE_TC
+    r = _run_prerecorded(SPECS[name], n=n, T=T, seed=7, engine=ENGINE_TC)
+    spec, sf = r["spec"], r["sf"]
+    assert rel_err(r["dseq"], torch.stack(r["deltas"])) <= REL_TOL
+    assert rel_err(r["xg"], r["x_ref"]) <= REL_TOL
+    for t in sorted({0, 1, T // 2, T}):
+        got = arena_to_state(r["ckpt"][t * sf * n:(t + 1) * sf * n].cpu(), spec.layers, n)
+        for (hg, cg), (hr, cr) in zip(got, r["states"][t]):
+            assert rel_err(hg, hr) <= REL_TOL and rel_err(cg, cr) <= REL_TOL, t
+    fin = arena_to_state(r["arena"].cpu(), spec.layers, n)
+    for (hg, cg), (hr, cr) in zip(fin, r["states"][T]):
+        assert rel_err(hg, hr) <= REL_TOL and rel_err(cg, cr) <= REL_TOL
+
+
+@pytest.mark.parametrize("T", [20, 100])
+def test_tc_fused_rastrigin_forward_then_bptt(T):
+    """BASELINE config #5 shape at reduced d: tcgen05 forward unroll (T=100: error growth over the full unroll)
+    feeding the BPTT kernel; both against the fp64 oracle."""
+    from open_l2o_b200.engine import ENGINE_TC, OPT_KINDS
+    spec = SPECS["dm_identity"]
+    n = 2000
+    gen = torch.Generator().manual_seed(5)
+    theta = _theta(spec, gain=0.05)
+    prob, x0 = _fused_problem("rastrigin_sep", n, gen)
+    prob64 = orc.FusedProblem("rastrigin_sep", prob.a.double(), prob.b.double(), prob.alpha, prob.fscale)
+    g64, res64 = orc.meta_grad(spec, theta.double(), x0.double(), orc.initial_state(spec, n, torch.float64), None, T,
+                               grad_of=prob64.f_and_g)
+    g32, res32 = orc.meta_grad(spec, theta, x0, orc.initial_state(spec, n), None, T, grad_of=prob.f_and_g)
+    h = make_handle(spec)
+    h.set_engine(ENGINE_TC)
+    sf = h.state_floats
+    th = theta.to(DEV)
+    arena = h.new_state(n, DEV)
+    ckpt = torch.zeros((T + 1) * sf * n, device=DEV)
+    x = x0.to(DEV).clone()
+    g_rec = torch.empty(T + 1, n, device=DEV)
+    fx = torch.zeros(T + 1, dtype=torch.float64, device=DEV)
+    h.unroll_fwd(th, n, T, arena, opt_kind=OPT_KINDS["rastrigin_sep"], opt_a=prob.a.to(DEV), opt_b=prob.b.to(DEV),
+                 opt_alpha=prob.alpha, opt_fscale=prob.fscale, x=x, ckpt=ckpt, g_rec=g_rec, fx=fx)
+    torch.cuda.synchronize()
+    slack = max(REL_TOL, 3.0 * rel_err(res32.x_final, res64.x_final))
+    assert rel_err(fx, res64.fx) <= slack
+    assert rel_err(x, res64.x_final) <= slack
+    dtheta = torch.zeros(h.n_theta, dtype=torch.float64, device=DEV)
+    h.unroll_bwd(th, n, T, g_rec, ckpt, dtheta, g_rec=g_rec)
+    torch.cuda.synchronize()
+    gslack = max(REL_TOL, 3.0 * rel_err(g32, g64))
+    assert rel_err(dtheta, g64) <= gslack, (rel_err(dtheta, g64), rel_err(g32, g64))
+
+
+def test_tc_matches_ffma_engine_large():
+    """Many tiles per CTA (persistent loop) + ragged tail: tcgen05 engine vs exact-fp32 engine."""
+    from open_l2o_b200.engine import ENGINE_FFMA, ENGINE_TC, OPT_KINDS
+    spec = SPECS["dm_identity"]
+    n, T = 148 * 256 * 2 + 333, 6
+    gen = torch.Generator().manual_seed(8)
+    theta = _theta(spec, gain=0.05).to(DEV)
+    a, b, x0 = (torch.randn(n, generator=gen).to(DEV) for _ in range(3))
+    outs = {}
+    for eng in (ENGINE_FFMA, ENGINE_TC):
+        h = make_handle(spec)
+        h.set_engine(eng)
+        arena = h.new_state(n, DEV)
+        x = x0.clone()
+        fx = torch.zeros(T + 1, dtype=torch.float64, device=DEV)
+        g_rec = torch.empty(T + 1, n, device=DEV)
+        h.unroll_fwd(theta, n, T, arena, opt_kind=OPT_KINDS["rastrigin_sep"], opt_a=a, opt_b=b, opt_alpha=10.0,
+                     opt_fscale=1.0 / n, x=x, g_rec=g_rec, fx=fx)
+        torch.cuda.synchronize()
+        outs[eng] = (x, arena, fx, g_rec)
+    for u, v in zip(outs[ENGINE_TC], outs[ENGINE_FFMA]):
+        assert rel_err(u, v) <= REL_TOL
