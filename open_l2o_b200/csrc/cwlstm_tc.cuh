@@ -181,13 +181,13 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
 __device__ __forceinline__ void lstm_units4(const float* z, float* c, float* h) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const float i = sigmoid_acc(z[4 * u + 0]);
-    const float j = tanh_acc(z[4 * u + 1]);
-    const float f = sigmoid_acc(z[4 * u + 2] + 1.0f);
-    const float o = sigmoid_acc(z[4 * u + 3]);
+    const float i = sigmoid_fast(z[4 * u + 0]);
+    const float j = tanh_fast(z[4 * u + 1]);
+    const float f = sigmoid_fast(z[4 * u + 2] + 1.0f);
+    const float o = sigmoid_fast(z[4 * u + 3]);
     const float cn = fmaf(f, c[u], i * j);
     c[u] = cn;
-    h[u] = tanh_acc(cn) * o;
+    h[u] = tanh_fast(cn) * o;
   }
 }
 

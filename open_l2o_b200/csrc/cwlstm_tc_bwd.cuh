@@ -1,0 +1,510 @@
+// tcgen05 BPTT kernel (sm_100a) for the LSTM-20x2 coordinate-wise optimizer (meta-loss mode).
+//
+// Per 128-coordinate tile and per time step (descending), every contraction runs on the tensor cores with
+// error-compensated 3xTF32 and fp32 accumulation in tensor memory:
+//   Z1 = A_F[0:32].B1, Z2 = A_F[0:48].B2      gate recompute from the checkpointed (h, c)   TS-mode (A in TMEM)
+//   dX2 = dZ2.W2^T (N=48), dX1 = dZ1.W1^T (N=32) TS-mode; B = the SAME forward weight image, addressed MN-major
+//   dW2^T += dZ2^T.X2, dW1^T += dZ1^T.X1        SS-mode over MN-major operands staged in shared memory by the
+//                                               epilogue threads; accumulators stay in TMEM for the whole kernel
+// CTA = one tile: 8 epilogue warps (thread pair per coordinate: hidden units 0..11 | 12..19) + 1 MMA-issuer warp.
+// Semantics: SURVEY.md Appendix B (derived from DM/meta.py:319-376, second_derivatives=False).
+#pragma once
+#include "cwlstm_tc.cuh"
+
+namespace l2o {
+namespace tcb {
+
+using namespace tc;
+
+constexpr int kEpi = 256;
+constexpr int kThreadsB = kEpi + 32;
+// TMEM column map
+constexpr int cD1 = 0;                   // Z1 accumulators (kept until the layer-1 backward re-reads them)
+constexpr int cD2 = 80;                  // Z2 accumulators, then dX2 / dX1 results (aliased)
+constexpr int cAFh = 160, cAFl = 208;    // forward A rows [u | 1 | . | h1 | h2], hi / lo
+constexpr int cAZh = 256, cAZl = 336;    // dZ rows (80 gate columns), hi / lo
+constexpr int cW2 = 416;                 // dW2^T accumulator: lanes = gate rows, 48 feature columns
+constexpr int cW1 = 464;                 // dW1^T accumulator: 32 feature columns
+static_assert(cW1 + 32 <= kTmemCols, "TMEM budget");
+constexpr int kXW = 48;                  // staged X row width (features)
+constexpr uint32_t kDzKBlock = (kN / 4) * 128;   // bytes per 8-coordinate block of staged dZ  (2560)
+constexpr uint32_t kXKBlock = (kXW / 4) * 128;   // bytes per 8-coordinate block of staged X   (1536)
+
+struct SmemB {
+  float img[kImgFloats];       // forward weight image (K-major); dX reads it MN-major
+  float dz_hi[128 * kN];       // MN-major staging: [c/8][gate/4][c%8][4]
+  float dz_lo[128 * kN];
+  float x_hi[128 * kXW];       // MN-major staging: [c/8][feature/4][c%8][4]
+  float x_lo[128 * kXW];
+  float wo[kH + 4];
+  uint64_t wbar, a_ready, d_ready, w_done;
+  uint32_t tmem_slot, pad;
+};
+
+__host__ __device__ constexpr uint32_t make_idesc_ex(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+  tc_wait_ld();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = __uint_as_float(r[k]);
+}
+__device__ __forceinline__ float4 split4_hi(const float* v, float4& lo) {
+  float h0, h1, h2, h3;
+  split_tf32(v[0], h0, lo.x);
+  split_tf32(v[1], h1, lo.y);
+  split_tf32(v[2], h2, lo.z);
+  split_tf32(v[3], h3, lo.w);
+  lo.x = to_tf32(lo.x); lo.y = to_tf32(lo.y); lo.z = to_tf32(lo.z); lo.w = to_tf32(lo.w);
+  return make_float4(h0, h1, h2, h3);
+}
+// 4 values -> TMEM A columns (hi/lo) and, optionally, the MN-major smem staging (hi/lo) at float index `sidx`
+__device__ __forceinline__ void put4(uint32_t t_hi, uint32_t t_lo, int col, const float* v, float* s_hi, float* s_lo,
+                                     int sidx, bool to_tmem, bool to_smem) {
+  float4 lo;
+  const float4 hi = split4_hi(v, lo);
+  if (to_tmem) {
+    tmem_st4(t_hi + col, hi.x, hi.y, hi.z, hi.w);
+    tmem_st4(t_lo + col, lo.x, lo.y, lo.z, lo.w);
+  }
+  if (to_smem) {
+    *reinterpret_cast<float4*>(s_hi + sidx) = hi;
+    *reinterpret_cast<float4*>(s_lo + sidx) = lo;
+  }
+}
+__device__ __forceinline__ int dz_sidx(int c, int unit) { return ((c >> 3) * (kN / 4) + unit) * 32 + (c & 7) * 4; }
+__device__ __forceinline__ int x_sidx(int c, int grp) { return ((c >> 3) * (kXW / 4) + grp) * 32 + (c & 7) * 4; }
+
+// activated gates of 4 units from 16 interleaved accumulator columns
+__device__ __forceinline__ void gates4(const float* z, float* g) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    g[4 * u + 0] = sigmoid_fast(z[4 * u + 0]);
+    g[4 * u + 1] = tanh_fast(z[4 * u + 1]);
+    g[4 * u + 2] = sigmoid_fast(z[4 * u + 2] + 1.0f);
+    g[4 * u + 3] = sigmoid_fast(z[4 * u + 3]);
+  }
+}
+// LSTM pointwise backward for one unit; g = (i, j, f, o) -> overwritten with (dz_i, dz_j, dz_f, dz_o)
+__device__ __forceinline__ void unit_bwd(float* g, float cprev, float tcn, float dh, float& dc) {
+  const float i = g[0], j = g[1], f = g[2], o = g[3];
+  const float d_o = dh * tcn;
+  const float dcv = fmaf(dh * o, 1.0f - tcn * tcn, dc);
+  g[0] = dcv * j * i * (1.0f - i);
+  g[1] = dcv * i * (1.0f - j * j);
+  g[2] = dcv * cprev * f * (1.0f - f);
+  g[3] = d_o * o * (1.0f - o);
+  dc = dcv * f;
+}
+
+template <class C, int HALF>
+__device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt, SmemB& S, uint32_t tmem_base, int warp,
+                                         int lane) {
+  constexpr int U0 = HALF == 0 ? 0 : 12;  // first hidden unit owned by this thread
+  constexpr int NU = HALF == 0 ? 12 : 8;  // number of owned units (multiples of 4: whole x16 accumulator loads)
+  const int q = warp & 3;
+  const int c = q * 32 + lane;  // coordinate within the tile == TMEM lane
+  const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+  const uint32_t tD1 = tl + cD1, tD2 = tl + cD2, tAFh = tl + cAFh, tAFl = tl + cAFl, tAZh = tl + cAZh, tAZl = tl + cAZl;
+  const int T = a.T;
+  const int64_t n = a.n;
+  const int64_t slot = n * C::SF;
+  const int64_t ntiles = (n + 127) / 128;
+  uint32_t pd = 0, pw = 0;
+  float acc_wo[NU], acc_bo = 0.f;
+#pragma unroll
+  for (int k = 0; k < NU; ++k) acc_wo[k] = 0.f;
+  // zero the persistent dW accumulators (lane = gate row)
+  if (HALF == 0) {
+#pragma unroll
+    for (int k = 0; k < (48 + 32) / 4; ++k) tmem_st4(tl + cW2 + 4 * k, 0.f, 0.f, 0.f, 0.f);
+  }
+  tc_wait_st();
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t i = tile * 128 + c;
+    const bool act = i < n;
+    float dh1c[NU], dc1c[NU], dh2c[NU], dc2c[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) { dh1c[k] = 0.f; dc1c[k] = 0.f; dh2c[k] = 0.f; dc2c[k] = 0.f; }
+    float lam = act ? a.g_rec[(int64_t)T * n + i] : 0.f;
+
+    for (int t = T - 1; t >= 0; --t) {
+      const float* ck = a.ckpt + (int64_t)t * slot;
+      // ---------------- P0: A_F <- [u | 1 | h1p | h2p] ----------------
+      float u4[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        float raw0 = act ? a.in_seq[(int64_t)t * n + i] : 0.f;
+        float uu[C::F];
+        preprocess<C>(nullptr, rt, raw0, 0.f, uu);
+#pragma unroll
+        for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
+        u4[C::F] = 1.0f;
+      }
+      float h2p[NU];
+      {
+        float h1p[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h2p[k] = 0.f; }
+        if (act) {
+          load_vec<NU>(ck + i * kH + U0, h1p);
+          load_vec<NU>(ck + 2 * n * kH + i * kH + U0, h2p);
+        }
+        if (HALF == 0) {
+          put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
+          tmem_st4(tAFh + 4, 0.f, 0.f, 0.f, 0.f);
+          tmem_st4(tAFl + 4, 0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int g4 = 0; g4 < NU / 4; ++g4) {
+          put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
+          put4(tAFh, tAFl, kColH2 + U0 + 4 * g4, h2p + 4 * g4, nullptr, nullptr, 0, true, false);
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&S.a_ready);
+      // ---------------- P1: h1n = LSTM1 forward (only what layer 2 needs) ----------------
+      float h1n[NU];
+      mbar_wait(&S.d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      {
+        float c1p[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) c1p[k] = 0.f;
+        if (act) load_vec<NU>(ck + (n + i) * kH + U0, c1p);
+#pragma unroll
+        for (int g4 = 0; g4 < NU / 4; ++g4) {
+          float z[16], g[16];
+          tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
+          gates4(z, g);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float cn = fmaf(g[4 * u + 2], c1p[4 * g4 + u], g[4 * u + 0] * g[4 * u + 1]);
+            h1n[4 * g4 + u] = tanh_fast(cn) * g[4 * u + 3];
+          }
+          put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1n + 4 * g4, nullptr, nullptr, 0, true, false);
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&S.a_ready);
+      // ---------------- P2: layer-2 forward recompute + output layer + layer-2 backward ----------------
+      mbar_wait(&S.d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      const float dy = rt.scale * lam;  // dDelta_t = sum_{tau>t} g_tau ; linear output (tanh_output handled by FFMA engine)
+      if (HALF == 0) acc_bo += dy;
+      // staging buffers must be free: the dW1 MMAs of the previous step have completed
+      mbar_wait(&S.w_done, pw ^ 1);
+      {
+        float c2p[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) c2p[k] = 0.f;
+        if (act) load_vec<NU>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
+#pragma unroll
+        for (int g4 = 0; g4 < NU / 4; ++g4) {
+          float z[16], g[16];
+          tmem_ld16(tD2 + 4 * U0 + 16 * g4, z);
+          gates4(z, g);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = 4 * g4 + u;
+            const float cn = fmaf(g[4 * u + 2], c2p[k], g[4 * u + 0] * g[4 * u + 1]);
+            const float tcn = tanh_fast(cn);
+            const float h2n = tcn * g[4 * u + 3];
+            acc_wo[k] = fmaf(h2n, dy, acc_wo[k]);
+            const float dh = fmaf(S.wo[U0 + k], dy, dh2c[k]);
+            unit_bwd(g + 4 * u, c2p[k], tcn, dh, dc2c[k]);
+            // dz of this unit: one 16-byte group of the MN-major staging + 4 TMEM columns
+            put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.dz_hi, S.dz_lo, dz_sidx(c, U0 + k), true, true);
+          }
+        }
+        // X2 row = [0.. 1 .. | h1n | h2p]
+        if (HALF == 0) {
+          float x0[4] = {0.f, 0.f, 0.f, 0.f};
+          x0[C::F] = 1.0f;
+          put4(0, 0, 0, x0, S.x_hi, S.x_lo, x_sidx(c, 0), false, true);
+          const float zz[4] = {0.f, 0.f, 0.f, 0.f};
+          put4(0, 0, 0, zz, S.x_hi, S.x_lo, x_sidx(c, 1), false, true);
+        }
+#pragma unroll
+        for (int g4 = 0; g4 < NU / 4; ++g4) {
+          put4(0, 0, 0, h1n + 4 * g4, S.x_hi, S.x_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
+          put4(0, 0, 0, h2p + 4 * g4, S.x_hi, S.x_lo, x_sidx(c, (kColH2 + U0) / 4 + g4), false, true);
+        }
+      }
+      fence_proxy_async();
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&S.a_ready);
+      // ---------------- P3: layer-1 backward ----------------
+      mbar_wait(&S.d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      float dh1[NU];
+#pragma unroll
+      for (int g4 = 0; g4 < NU / 4; ++g4) {
+        float v[4];
+        tmem_ld4(tD2 + kColH1 + U0 + 4 * g4, v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dh1[4 * g4 + u] = v[u] + dh1c[4 * g4 + u];
+        tmem_ld4(tD2 + kColH2 + U0 + 4 * g4, v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dh2c[4 * g4 + u] = v[u];
+      }
+      mbar_wait(&S.w_done, pw);  // dW2 MMAs done: staging may be overwritten
+      pw ^= 1;
+      {
+        float c1p[NU], h1p[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) { c1p[k] = 0.f; h1p[k] = 0.f; }
+        if (act) {
+          load_vec<NU>(ck + (n + i) * kH + U0, c1p);
+          load_vec<NU>(ck + i * kH + U0, h1p);
+        }
+#pragma unroll
+        for (int g4 = 0; g4 < NU / 4; ++g4) {
+          float z[16], g[16];
+          tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
+          gates4(z, g);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = 4 * g4 + u;
+            const float cn = fmaf(g[4 * u + 2], c1p[k], g[4 * u + 0] * g[4 * u + 1]);
+            const float tcn = tanh_fast(cn);
+            unit_bwd(g + 4 * u, c1p[k], tcn, dh1[k], dc1c[k]);
+            put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.dz_hi, S.dz_lo, dz_sidx(c, U0 + k), true, true);
+          }
+          put4(0, 0, 0, h1p + 4 * g4, S.x_hi, S.x_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
+        }
+        if (HALF == 0) {
+          put4(0, 0, 0, u4, S.x_hi, S.x_lo, x_sidx(c, 0), false, true);
+          const float zz[4] = {0.f, 0.f, 0.f, 0.f};
+          put4(0, 0, 0, zz, S.x_hi, S.x_lo, x_sidx(c, 1), false, true);
+        }
+      }
+      fence_proxy_async();
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&S.a_ready);
+      // ---------------- P4: carry for step t-1 ----------------
+      mbar_wait(&S.d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int g4 = 0; g4 < NU / 4; ++g4) {
+        float v[4];
+        tmem_ld4(tD2 + kColH1 + U0 + 4 * g4, v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dh1c[4 * g4 + u] = v[u];
+      }
+      if (act) lam += a.g_rec[(int64_t)t * n + i];
+    }
+  }
+  // ---------------- flush: output-layer gradient from registers ----------------
+#pragma unroll
+  for (int k = 0; k < NU; ++k) {
+    float v = acc_wo[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(&a.dtheta[C::O_WO + U0 + k], (double)v);
+  }
+  if (HALF == 0) {
+    float v = acc_bo;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(&a.dtheta[C::O_BO], (double)v);
+  }
+  // ---------------- flush: dW^T accumulators (lane = interleaved gate row) ----------------
+  mbar_wait(&S.w_done, pw ^ 1);  // last dW1 MMAs complete
+  tc_fence_after();
+  if (HALF == 0) {
+    const int m = c;  // gate row 4u+g
+    const int col = (m & 3) * kH + (m >> 2);
+#pragma unroll
+    for (int k4 = 0; k4 < 48 / 4; ++k4) {
+      float v[4];
+      tmem_ld4(tl + cW2 + 4 * k4, v);
+      if (m < kN) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 4 * k4 + e;
+          int idx = -1;
+          if (k == C::F) idx = C::O_B2 + col;
+          else if (k >= kColH1 && k < kColH1 + 2 * kH) idx = C::O_W2 + (k - kColH1) * C::G2 + col;
+          if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k4 = 0; k4 < 32 / 4; ++k4) {
+      float v[4];
+      tmem_ld4(tl + cW1 + 4 * k4, v);
+      if (m < kN) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 4 * k4 + e;
+          int idx = -1;
+          if (k < C::F) idx = C::O_W1 + k * C::G1 + col;
+          else if (k == C::F) idx = C::O_B1 + col;
+          else if (k >= kColH1 && k < kColH1 + kH) idx = C::O_W1 + (C::F + k - kColH1) * C::G1 + col;
+          if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
+        }
+      }
+    }
+  }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a, NetRt rt, const float* __restrict__ img) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemB& S = *reinterpret_cast<SmemB*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.T;
+  const int64_t ntiles = (a.n + 127) / 128;
+
+  for (int k = threadIdx.x; k < 128 * kN; k += blockDim.x) { S.dz_hi[k] = 0.f; S.dz_lo[k] = 0.f; }
+  for (int k = threadIdx.x; k < 128 * kXW; k += blockDim.x) { S.x_hi[k] = 0.f; S.x_lo[k] = 0.f; }
+  if (threadIdx.x < kH) S.wo[threadIdx.x] = a.theta[C::O_WO + threadIdx.x];
+  if (warp == kEpi / 32) {
+    if (lane == 0) {
+      mbar_init(&S.wbar, 1);
+      mbar_init(&S.a_ready, kEpi);
+      mbar_init(&S.d_ready, 1);
+      mbar_init(&S.w_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&S.tmem_slot, kTmemCols);
+    tmem_relinquish();
+    if (lane == 0) {
+      mbar_expect_tx(&S.wbar, kImgBytes);
+      tma_bulk_g2s(S.img, img, kImgBytes, &S.wbar);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_slot;
+
+  if (warp < kEpi / 32) {
+    if (warp < 4) epilogue<C, 0>(a, rt, S, tmem_base, warp, lane);
+    else epilogue<C, 1>(a, rt, S, tmem_base, warp, lane);
+  } else {
+    mbar_wait(&S.wbar, 0);
+    if (lane == 0) {
+      const uint32_t img_s = smem_u32(S.img);
+      // forward (K-major) views
+      const uint64_t b1h = make_bdesc(img_s), b1l = make_bdesc(img_s + kB1Floats * 4);
+      const uint64_t b2h = make_bdesc(img_s + 2 * kB1Floats * 4), b2l = make_bdesc(img_s + (2 * kB1Floats + kB2Floats) * 4);
+      // transposed (MN-major) views of the same images: MN-group (input/4) stride = kLBO, K-group (gate/8) stride = kSBO
+      const uint64_t t1h = make_desc(img_s, kSBO, kLBO), t1l = make_desc(img_s + kB1Floats * 4, kSBO, kLBO);
+      const uint64_t t2h = make_desc(img_s + 2 * kB1Floats * 4, kSBO, kLBO);
+      const uint64_t t2l = make_desc(img_s + (2 * kB1Floats + kB2Floats) * 4, kSBO, kLBO);
+      // staged operands (MN-major): MN-group stride 128 B, K-group (8 coordinates) stride = block size
+      const uint64_t dzh = make_desc(smem_u32(S.dz_hi), kDzKBlock, 128), dzl = make_desc(smem_u32(S.dz_lo), kDzKBlock, 128);
+      const uint64_t xh = make_desc(smem_u32(S.x_hi), kXKBlock, 128), xl = make_desc(smem_u32(S.x_lo), kXKBlock, 128);
+      constexpr uint32_t id_fwd = make_idesc_ex(kN, 0, 0);
+      constexpr uint32_t id_dx2 = make_idesc_ex(48, 0, 1), id_dx1 = make_idesc_ex(32, 0, 1);
+      constexpr uint32_t id_dw2 = make_idesc_ex(48, 1, 1), id_dw1 = make_idesc_ex(32, 1, 1);
+      constexpr uint64_t kFwdStep = (2 * kLBO) >> 4;      // K-major: 8 k = two 16-byte chunks
+      constexpr uint64_t kTrStep = kSBO >> 4;             // transposed view: 8 gates = one n/8 group
+      constexpr uint64_t kDzStep = kDzKBlock >> 4, kXStep = kXKBlock >> 4;
+      const uint32_t tD1 = tmem_base + cD1, tD2 = tmem_base + cD2, tAFh = tmem_base + cAFh, tAFl = tmem_base + cAFl;
+      const uint32_t tAZh = tmem_base + cAZh, tAZl = tmem_base + cAZl, tW2 = tmem_base + cW2, tW1 = tmem_base + cW1;
+      uint32_t pa = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int t = T - 1; t >= 0; --t) {
+          // Z1
+          mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
+          for (int kc = 0; kc < kK1 / 8; ++kc) {
+            mma_tf32_ts(tD1, tAFl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+            mma_tf32_ts(tD1, tAFh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
+            mma_tf32_ts(tD1, tAFh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
+          }
+          tc_commit(&S.d_ready);
+          // Z2
+          mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
+          for (int kc = 0; kc < kK2 / 8; ++kc) {
+            mma_tf32_ts(tD2, tAFl + 8 * kc, b2h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+            mma_tf32_ts(tD2, tAFh + 8 * kc, b2l + kc * kFwdStep, id_fwd, 1u);
+            mma_tf32_ts(tD2, tAFh + 8 * kc, b2h + kc * kFwdStep, id_fwd, 1u);
+          }
+          tc_commit(&S.d_ready);
+          // dX2 = dZ2 . W2^T   and   dW2^T += dZ2^T . X2
+          mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
+          for (int kc = 0; kc < kN / 8; ++kc) {
+            mma_tf32_ts(tD2, tAZl + 8 * kc, t2h + kc * kTrStep, id_dx2, kc > 0 ? 1u : 0u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t2l + kc * kTrStep, id_dx2, 1u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t2h + kc * kTrStep, id_dx2, 1u);
+          }
+          tc_commit(&S.d_ready);
+          for (int kb = 0; kb < 16; ++kb) {
+            mma_tf32_ss(tW2, dzl + kb * kDzStep, xh + kb * kXStep, id_dw2, 1u);
+            mma_tf32_ss(tW2, dzh + kb * kDzStep, xl + kb * kXStep, id_dw2, 1u);
+            mma_tf32_ss(tW2, dzh + kb * kDzStep, xh + kb * kXStep, id_dw2, 1u);
+          }
+          tc_commit(&S.w_done);
+          // dX1 = dZ1 . W1^T   and   dW1^T += dZ1^T . X1
+          mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
+          for (int kc = 0; kc < kN / 8; ++kc) {
+            mma_tf32_ts(tD2, tAZl + 8 * kc, t1h + kc * kTrStep, id_dx1, kc > 0 ? 1u : 0u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t1l + kc * kTrStep, id_dx1, 1u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t1h + kc * kTrStep, id_dx1, 1u);
+          }
+          tc_commit(&S.d_ready);
+          for (int kb = 0; kb < 16; ++kb) {
+            mma_tf32_ss(tW1, dzl + kb * kDzStep, xh + kb * kXStep, id_dw1, 1u);
+            mma_tf32_ss(tW1, dzh + kb * kDzStep, xl + kb * kXStep, id_dw1, 1u);
+            mma_tf32_ss(tW1, dzh + kb * kDzStep, xh + kb * kXStep, id_dw1, 1u);
+          }
+          tc_commit(&S.w_done);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == kEpi / 32) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tcb
+
+template <class C>
+int tc_launch_bwd(const NetRt& rt, const l2o_bwd_args& a, float* img, cudaStream_t st, int sms) {
+  tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img);
+  auto k = tcb::unroll_bwd_kernel<C>;
+  const size_t smem = sizeof(tcb::SmemB) + 128;
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
+  const int64_t ntiles = (a.n + 127) / 128;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  k<<<grid, tcb::kThreadsB, smem, st>>>(a, rt, img);
+  return cudaGetLastError() == cudaSuccess ? L2O_OK : L2O_E_CUDA;
+}
+
+}  // namespace l2o

@@ -6,7 +6,7 @@
 namespace l2o {
 bool tc_supported(int cfg) { return cfg == 0 || cfg == 1; }  // LSTM-20x2 with identity / LogAndSign preprocessing
 bool tc_fwd_ok(const l2o_unroll_args& a) { return a.m == nullptr && a.feat_rec == nullptr; }
-bool tc_auto_default() { return false; }  // flipped to true once the engine is parity-green on the B200
+bool tc_auto_default() { return true; }  // parity-green on the B200 (tests/test_tc_gpu.py): AUTO prefers tcgen05
 
 int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st) {
   if (!tc_supported(h->cfg) || !tc_fwd_ok(a)) return L2O_E_UNSUPPORTED;
