@@ -25,18 +25,23 @@ constexpr int kEpiThreads = 128 * kTiles;
 constexpr int kThreads = kEpiThreads + 32;   // + MMA / alloc warp
 constexpr int kH = 20;
 constexpr int kN = 4 * kH;                   // 80 gate columns
-constexpr int kXC = 8;                       // feature chunk: cols [0, kXC): features, then the constant 1
-constexpr int kColH1 = kXC;                  // A columns of h1
-constexpr int kColH2 = kXC + kH;             // A columns of h2
-constexpr int kACols = kXC + 2 * kH;         // 48
-constexpr int kK1 = 32;                      // layer-1 K range: cols [0, 32)  (4 zero-weight cols of h2)
-constexpr int kK2 = 48;                      // layer-2 K range: cols [0, 48)  (feature rows zero, 1-col = b2)
+constexpr int kXC = 4;                       // feature chunk: cols [0, kXC): features, then the constant 1
+constexpr int kColH1 = kXC;                  // A columns of h1: [4, 24)
+constexpr int kColH2 = kXC + kH;             // A columns of h2: [24, 44)
+constexpr int kACols = 48;                   // 44 used + 4 zero pad columns
+constexpr int kK1 = 24;                      // layer-1 K range: cols [0, 24) = [features | 1 | h1]
+constexpr int kK2 = 48;                      // layer-2 K range: cols [0, 48)  (feature rows zero, 1-col = b2, pad rows zero)
 constexpr int kTileCols = kN + 2 * kACols;   // D | A_hi | A_lo = 176 TMEM columns per tile
 constexpr int kTmemCols = 512;
-constexpr int kB1Floats = kK1 * kN;          // 2560
+constexpr int kB1Floats = kK1 * kN;          // 1920
 constexpr int kB2Floats = kK2 * kN;          // 3840
-constexpr int kImgFloats = 2 * (kB1Floats + kB2Floats);  // B1h | B1l | B2h | B2l
-constexpr int kImgBytes = kImgFloats * 4;    // 51200
+constexpr int kImgFloats = 2 * (kB1Floats + kB2Floats);  // forward image: B1h | B1l | B2h | B2l
+constexpr int kImgBytes = kImgFloats * 4;    // 46080
+// transposed (input-major) images for the BPTT dX contractions: T[n' = input][k' = gate], K-major
+constexpr int kT1Rows = 32, kT2Rows = 48;
+constexpr int kT1Floats = kT1Rows * kN, kT2Floats = kT2Rows * kN;
+constexpr int kImgAllFloats = kImgFloats + 2 * (kT1Floats + kT2Floats);  // + T1h | T1l | T2h | T2l
+constexpr int kImgAllBytes = kImgAllFloats * 4;  // 97280
 constexpr uint32_t kSBO = 128;               // bytes between 8-row (N) core-matrix groups
 constexpr uint32_t kLBO = (kN / 8) * 128;    // bytes between 16-byte K chunks
 
@@ -146,33 +151,61 @@ __device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
 // MMA column n = 4*u + gate (gate 0..3 = i,j,f,o of hidden unit u) -- one tcgen05.ld x16 = 4 whole units.
 __device__ __forceinline__ int img_index(int k, int n) { return ((k >> 2) * (kN / 8) + (n >> 3)) * 32 + (n & 7) * 4 + (k & 3); }
 
+// transposed image index: rows n' (inputs, NR of them), K = gate (kN): ((k'/4)*(NR/8) + n'/8)*32 + (n'%8)*4 + k'%4
+__device__ __forceinline__ int timg_index(int nrows, int nprime, int kprime) {
+  return ((kprime >> 2) * (nrows / 8) + (nprime >> 3)) * 32 + (nprime & 7) * 4 + (kprime & 3);
+}
+
+// value of the extended weight matrix of layer `l2` at (input row k = A column index, interleaved gate column n)
 template <class C>
-__global__ void prep_weights_kernel(const float* __restrict__ theta, float* __restrict__ img) {
+__device__ __forceinline__ float ext_weight(const float* __restrict__ theta, bool l2, int k, int n) {
+  const int u = n >> 2, g = n & 3;
+  const int col = g * kH + u;  // reference gate-column order i|j|f|o blocks (snt.LSTM split)
+  if (!l2) {
+    if (k < C::F) return theta[C::O_W1 + k * C::G1 + col];
+    if (k == C::F) return theta[C::O_B1 + col];
+    if (k >= kColH1 && k < kColH1 + kH) return theta[C::O_W1 + (C::F + k - kColH1) * C::G1 + col];
+    return 0.f;
+  }
+  if (k == C::F) return theta[C::O_B2 + col];
+  if (k >= kColH1 && k < kColH1 + 2 * kH) return theta[C::O_W2 + (k - kColH1) * C::G2 + col];
+  return 0.f;
+}
+
+template <class C>
+__global__ void prep_weights_kernel(const float* __restrict__ theta, float* __restrict__ img, int with_transposed) {
   static_assert(C::H1 == kH && C::H2 == kH && C::F <= 3 && !C::FC, "tc engine: LSTM-20x2, F <= 3");
   float* b1h = img;
   float* b1l = img + kB1Floats;
   float* b2h = img + 2 * kB1Floats;
   float* b2l = img + 2 * kB1Floats + kB2Floats;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < (kK1 + kK2) * kN; e += gridDim.x * blockDim.x) {
-    const bool l2 = e >= kK1 * kN;
-    const int ee = l2 ? e - kK1 * kN : e;
-    const int k = ee / kN, n = ee % kN;
-    const int u = n >> 2, g = n & 3;
-    const int col = g * kH + u;  // reference gate-column order i|j|f|o blocks (snt.LSTM split)
-    float w = 0.f;
-    if (!l2) {
-      if (k < C::F) w = theta[C::O_W1 + k * C::G1 + col];
-      else if (k == C::F) w = theta[C::O_B1 + col];
-      else if (k >= kColH1 && k < kColH1 + kH) w = theta[C::O_W1 + (C::F + k - kColH1) * C::G1 + col];
-    } else {
-      if (k == C::F) w = theta[C::O_B2 + col];
-      else if (k >= kColH1 && k < kColH1 + 2 * kH) w = theta[C::O_W2 + (k - kColH1) * C::G2 + col];
-    }
+  float* t1h = img + kImgFloats;
+  float* t1l = t1h + kT1Floats;
+  float* t2h = t1l + kT1Floats;
+  float* t2l = t2h + kT2Floats;
+  const int nfwd = (kK1 + kK2) * kN;
+  const int ntr = with_transposed ? (kT1Rows + kT2Rows) * kN : 0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nfwd + ntr; e += gridDim.x * blockDim.x) {
     float hi, lo;
-    split_tf32(w, hi, lo);
-    const int idx = img_index(k, n);
-    (l2 ? b2h : b1h)[idx] = hi;
-    (l2 ? b2l : b1l)[idx] = to_tf32(lo);
+    if (e < nfwd) {
+      const bool l2 = e >= kK1 * kN;
+      const int ee = l2 ? e - kK1 * kN : e;
+      const int k = ee / kN, n = ee % kN;
+      split_tf32(ext_weight<C>(theta, l2, k, n), hi, lo);
+      const int idx = img_index(k, n);
+      (l2 ? b2h : b1h)[idx] = hi;
+      (l2 ? b2l : b1l)[idx] = to_tf32(lo);
+    } else {
+      const int e2 = e - nfwd;
+      const bool l2 = e2 >= kT1Rows * kN;
+      const int ee = l2 ? e2 - kT1Rows * kN : e2;
+      const int k = ee / kN, n = ee % kN;  // k = input row (n'), n = gate (k')
+      const float w = (k < (l2 ? kK2 : kK1)) ? ext_weight<C>(theta, l2, k, n) : 0.f;
+      split_tf32(w, hi, lo);
+      const int idx = timg_index(l2 ? kT2Rows : kT1Rows, k, n);
+      (l2 ? t2h : t1h)[idx] = hi;
+      (l2 ? t2l : t1l)[idx] = to_tf32(lo);
+    }
   }
 }
 
@@ -261,6 +294,9 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
     uint32_t pd = 0;  // d_ready parity
     const int64_t slot = n * C::SF;
     double imit = 0.0;
+    // zero the 4 pad columns of A once (they meet zero weight rows, but must be finite)
+    tmem_st4(t_ah + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
+    tmem_st4(t_al + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int64_t i = pair * kEpiThreads + tile * 128 + (warp & 3) * 32 + lane;
       const bool act = i < n;
@@ -309,8 +345,6 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
           for (int k = 0; k < C::F; ++k) u[k] = dummy[k];
           u[C::F] = 1.0f;  // bias column
           st_split4(t_ah, t_al, 0, u);
-          tmem_st4(t_ah + 4, 0.f, 0.f, 0.f, 0.f);
-          tmem_st4(t_al + 4, 0.f, 0.f, 0.f, 0.f);
         }
         tc_wait_st();
         tc_fence_before();
@@ -451,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
 // ------------------------------------------------------------------ host side (called from l2o_capi.cu)
 template <class C>
 int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms) {
-  tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img);
+  tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 0);
   auto k = tc::unroll_fwd_kernel<C>;
   const size_t smem = sizeof(tc::Smem) + (size_t)(a.T + 1) * sizeof(double) + 128;
   if (smem > 220 * 1024) return L2O_E_INVALID;

@@ -26,27 +26,35 @@ constexpr int cAZh = 256, cAZl = 336;    // dZ rows (80 gate columns), hi / lo
 constexpr int cW2 = 416;                 // dW2^T accumulator: lanes = gate rows, 48 feature columns
 constexpr int cW1 = 464;                 // dW1^T accumulator: 32 feature columns
 static_assert(cW1 + 32 <= kTmemCols, "TMEM budget");
-constexpr int kXW = 48;                  // staged X row width (features)
-constexpr uint32_t kDzKBlock = (kN / 4) * 128;   // bytes per 8-coordinate block of staged dZ  (2560)
-constexpr uint32_t kXKBlock = (kXW / 4) * 128;   // bytes per 8-coordinate block of staged X   (1536)
+// Staged operand Y = [X (48 feature slots) | dZ (80 gate slots)] per coordinate, MN-major SWIZZLE_128B_BASE32B
+// (the only shared-memory layout the tensor core accepts for MN-major tf32; address map verified on the B200 with
+// scripts/umma_probe.cu):  byte(mn, c) = (c/4)*kYSBO + (mn/32)*kYLBO + (c%4)*128 + (((mn%32)/8) ^ (c%4))*32 + (mn%8)*4
+// The SAME buffer is the A operand (M = 128 slots) and the B operand (N = 48 / 32 feature slots) of
+// dW^T-block = Y^T.Y : rows 48..127 (gate slots) x cols 0..47 (feature slots) is dZ^T.X.
+constexpr int kYSlots = 128;
+constexpr int kYX = 0, kYZ = 48;                 // slot bases of X and dZ inside a Y row
+constexpr uint32_t kYLBO = 512;                  // bytes between 32-slot MN atoms
+constexpr uint32_t kYSBO = 4 * 512;              // bytes between 4-coordinate K atoms
+constexpr int kYFloats = 128 * kYSlots;          // 16384 floats = 64 KB per hi / lo buffer
 
 struct SmemB {
-  float img[kImgFloats];       // forward weight image (K-major); dX reads it MN-major
-  float dz_hi[128 * kN];       // MN-major staging: [c/8][gate/4][c%8][4]
-  float dz_lo[128 * kN];
-  float x_hi[128 * kXW];       // MN-major staging: [c/8][feature/4][c%8][4]
-  float x_lo[128 * kXW];
+  float y_hi[kYFloats];        // 1024-B aligned (first member)
+  float y_lo[kYFloats];
+  float img[kImgAllFloats];    // B1h|B1l|B2h|B2l (forward, K-major) | T1h|T1l|T2h|T2l (transposed, K-major)
   float wo[kH + 4];
   uint64_t wbar, a_ready, d_ready, w_done;
   uint32_t tmem_slot, pad;
 };
+static_assert(sizeof(SmemB) + 1024 <= 227 * 1024, "shared memory budget");
 
 __host__ __device__ constexpr uint32_t make_idesc_ex(int n, int a_mn, int b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+// layout_type: 0 = no swizzle (interleave), 1 = SWIZZLE_128B_BASE32B   (cute::UMMA::LayoutType)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -92,8 +100,12 @@ __device__ __forceinline__ void put4(uint32_t t_hi, uint32_t t_lo, int col, cons
     *reinterpret_cast<float4*>(s_lo + sidx) = lo;
   }
 }
-__device__ __forceinline__ int dz_sidx(int c, int unit) { return ((c >> 3) * (kN / 4) + unit) * 32 + (c & 7) * 4; }
-__device__ __forceinline__ int x_sidx(int c, int grp) { return ((c >> 3) * (kXW / 4) + grp) * 32 + (c & 7) * 4; }
+// float index of the 16-byte group holding slots [mn, mn+4) (mn % 4 == 0) of coordinate c in a Y buffer
+__device__ __forceinline__ int y_sidx(int c, int mn) {
+  return (c >> 2) * (int)(kYSBO / 4) + (mn >> 5) * (int)(kYLBO / 4) + (c & 3) * 32 + ((((mn & 31) >> 3) ^ (c & 3)) << 3) + (mn & 7);
+}
+__device__ __forceinline__ int dz_sidx(int c, int unit) { return y_sidx(c, kYZ + 4 * unit); }
+__device__ __forceinline__ int x_sidx(int c, int grp) { return y_sidx(c, kYX + 4 * grp); }
 
 // activated gates of 4 units from 16 interleaved accumulator columns
 __device__ __forceinline__ void gates4(const float* z, float* g) {
@@ -130,7 +142,8 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
   const int64_t n = a.n;
   const int64_t slot = n * C::SF;
   const int64_t ntiles = (n + 127) / 128;
-  uint32_t pd = 0, pw = 0;
+  uint32_t pd = 0;
+  // w_done completes exactly twice per step: dW2 (even completion, parity 0) then dW1 (odd, parity 1)
   float acc_wo[NU], acc_bo = 0.f;
 #pragma unroll
   for (int k = 0; k < NU; ++k) acc_wo[k] = 0.f;
@@ -138,6 +151,8 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
   if (HALF == 0) {
 #pragma unroll
     for (int k = 0; k < (48 + 32) / 4; ++k) tmem_st4(tl + cW2 + 4 * k, 0.f, 0.f, 0.f, 0.f);
+    tmem_st4(tAFh + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);  // A pad columns 44..47: zero weights, must be finite
+    tmem_st4(tAFl + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
   }
   tc_wait_st();
 
@@ -170,11 +185,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
           load_vec<NU>(ck + i * kH + U0, h1p);
           load_vec<NU>(ck + 2 * n * kH + i * kH + U0, h2p);
         }
-        if (HALF == 0) {
-          put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
-          tmem_st4(tAFh + 4, 0.f, 0.f, 0.f, 0.f);
-          tmem_st4(tAFl + 4, 0.f, 0.f, 0.f, 0.f);
-        }
+        if (HALF == 0) put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
           put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
@@ -217,7 +228,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       const float dy = rt.scale * lam;  // dDelta_t = sum_{tau>t} g_tau ; linear output (tanh_output handled by FFMA engine)
       if (HALF == 0) acc_bo += dy;
       // staging buffers must be free: the dW1 MMAs of the previous step have completed
-      mbar_wait(&S.w_done, pw ^ 1);
+      mbar_wait(&S.w_done, 1);  // passes trivially on the fresh barrier (first step)
       {
         float c2p[NU];
 #pragma unroll
@@ -238,21 +249,19 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
             const float dh = fmaf(S.wo[U0 + k], dy, dh2c[k]);
             unit_bwd(g + 4 * u, c2p[k], tcn, dh, dc2c[k]);
             // dz of this unit: one 16-byte group of the MN-major staging + 4 TMEM columns
-            put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.dz_hi, S.dz_lo, dz_sidx(c, U0 + k), true, true);
+            put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.y_hi, S.y_lo, dz_sidx(c, U0 + k), true, true);
           }
         }
         // X2 row = [0.. 1 .. | h1n | h2p]
         if (HALF == 0) {
           float x0[4] = {0.f, 0.f, 0.f, 0.f};
           x0[C::F] = 1.0f;
-          put4(0, 0, 0, x0, S.x_hi, S.x_lo, x_sidx(c, 0), false, true);
-          const float zz[4] = {0.f, 0.f, 0.f, 0.f};
-          put4(0, 0, 0, zz, S.x_hi, S.x_lo, x_sidx(c, 1), false, true);
+          put4(0, 0, 0, x0, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
         }
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
-          put4(0, 0, 0, h1n + 4 * g4, S.x_hi, S.x_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
-          put4(0, 0, 0, h2p + 4 * g4, S.x_hi, S.x_lo, x_sidx(c, (kColH2 + U0) / 4 + g4), false, true);
+          put4(0, 0, 0, h1n + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
+          put4(0, 0, 0, h2p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH2 + U0) / 4 + g4), false, true);
         }
       }
       fence_proxy_async();
@@ -274,8 +283,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 #pragma unroll
         for (int u = 0; u < 4; ++u) dh2c[4 * g4 + u] = v[u];
       }
-      mbar_wait(&S.w_done, pw);  // dW2 MMAs done: staging may be overwritten
-      pw ^= 1;
+      mbar_wait(&S.w_done, 0);  // dW2 MMAs done: staging may be overwritten
       {
         float c1p[NU], h1p[NU];
 #pragma unroll
@@ -295,15 +303,11 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
             const float cn = fmaf(g[4 * u + 2], c1p[k], g[4 * u + 0] * g[4 * u + 1]);
             const float tcn = tanh_fast(cn);
             unit_bwd(g + 4 * u, c1p[k], tcn, dh1[k], dc1c[k]);
-            put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.dz_hi, S.dz_lo, dz_sidx(c, U0 + k), true, true);
+            put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.y_hi, S.y_lo, dz_sidx(c, U0 + k), true, true);
           }
-          put4(0, 0, 0, h1p + 4 * g4, S.x_hi, S.x_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
+          put4(0, 0, 0, h1p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
         }
-        if (HALF == 0) {
-          put4(0, 0, 0, u4, S.x_hi, S.x_lo, x_sidx(c, 0), false, true);
-          const float zz[4] = {0.f, 0.f, 0.f, 0.f};
-          put4(0, 0, 0, zz, S.x_hi, S.x_lo, x_sidx(c, 1), false, true);
-        }
+        if (HALF == 0) put4(0, 0, 0, u4, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
       }
       fence_proxy_async();
       tc_wait_st();
@@ -338,16 +342,16 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
     if (lane == 0) atomicAdd(&a.dtheta[C::O_BO], (double)v);
   }
   // ---------------- flush: dW^T accumulators (lane = interleaved gate row) ----------------
-  mbar_wait(&S.w_done, pw ^ 1);  // last dW1 MMAs complete
+  mbar_wait(&S.w_done, 1);  // last dW1 MMAs complete
   tc_fence_after();
   if (HALF == 0) {
-    const int m = c;  // gate row 4u+g
+    const int m = c - kYZ;  // Y slot -> interleaved gate row 4u+g (slots below kYZ hold the unused X^T.X block)
     const int col = (m & 3) * kH + (m >> 2);
 #pragma unroll
     for (int k4 = 0; k4 < 48 / 4; ++k4) {
       float v[4];
       tmem_ld4(tl + cW2 + 4 * k4, v);
-      if (m < kN) {
+      if (m >= 0 && m < kN) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = 4 * k4 + e;
@@ -362,7 +366,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
     for (int k4 = 0; k4 < 32 / 4; ++k4) {
       float v[4];
       tmem_ld4(tl + cW1 + 4 * k4, v);
-      if (m < kN) {
+      if (m >= 0 && m < kN) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = 4 * k4 + e;
@@ -379,14 +383,13 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 
 template <class C>
 __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a, NetRt rt, const float* __restrict__ img) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemB& S = *reinterpret_cast<SmemB*>(smem_raw);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  SmemB& S = *reinterpret_cast<SmemB*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = a.T;
   const int64_t ntiles = (a.n + 127) / 128;
 
-  for (int k = threadIdx.x; k < 128 * kN; k += blockDim.x) { S.dz_hi[k] = 0.f; S.dz_lo[k] = 0.f; }
-  for (int k = threadIdx.x; k < 128 * kXW; k += blockDim.x) { S.x_hi[k] = 0.f; S.x_lo[k] = 0.f; }
+  for (int k = threadIdx.x; k < kYFloats; k += blockDim.x) { S.y_hi[k] = 0.f; S.y_lo[k] = 0.f; }
   if (threadIdx.x < kH) S.wo[threadIdx.x] = a.theta[C::O_WO + threadIdx.x];
   if (warp == kEpi / 32) {
     if (lane == 0) {
@@ -400,8 +403,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
     tmem_alloc(&S.tmem_slot, kTmemCols);
     tmem_relinquish();
     if (lane == 0) {
-      mbar_expect_tx(&S.wbar, kImgBytes);
-      tma_bulk_g2s(S.img, img, kImgBytes, &S.wbar);
+      mbar_expect_tx(&S.wbar, kImgAllBytes);
+      tma_bulk_g2s(S.img, img, kImgAllBytes, &S.wbar);
     }
   }
   fence_proxy_async();
@@ -420,19 +423,20 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
       // forward (K-major) views
       const uint64_t b1h = make_bdesc(img_s), b1l = make_bdesc(img_s + kB1Floats * 4);
       const uint64_t b2h = make_bdesc(img_s + 2 * kB1Floats * 4), b2l = make_bdesc(img_s + (2 * kB1Floats + kB2Floats) * 4);
-      // transposed (MN-major) views of the same images: MN-group (input/4) stride = kLBO, K-group (gate/8) stride = kSBO
-      const uint64_t t1h = make_desc(img_s, kSBO, kLBO), t1l = make_desc(img_s + kB1Floats * 4, kSBO, kLBO);
-      const uint64_t t2h = make_desc(img_s + 2 * kB1Floats * 4, kSBO, kLBO);
-      const uint64_t t2l = make_desc(img_s + (2 * kB1Floats + kB2Floats) * 4, kSBO, kLBO);
-      // staged operands (MN-major): MN-group stride 128 B, K-group (8 coordinates) stride = block size
-      const uint64_t dzh = make_desc(smem_u32(S.dz_hi), kDzKBlock, 128), dzl = make_desc(smem_u32(S.dz_lo), kDzKBlock, 128);
-      const uint64_t xh = make_desc(smem_u32(S.x_hi), kXKBlock, 128), xl = make_desc(smem_u32(S.x_lo), kXKBlock, 128);
+      // transposed images (K-major, no swizzle): T[n' = input][k' = gate]; 16-byte K chunk stride = (rows/8)*128
+      const uint32_t t_s = img_s + kImgFloats * 4;
+      constexpr uint32_t kT1LBO = (kT1Rows / 8) * 128, kT2LBO = (kT2Rows / 8) * 128;
+      const uint64_t t1h = make_desc(t_s, kT1LBO, 128), t1l = make_desc(t_s + kT1Floats * 4, kT1LBO, 128);
+      const uint64_t t2h = make_desc(t_s + 2 * kT1Floats * 4, kT2LBO, 128);
+      const uint64_t t2l = make_desc(t_s + (2 * kT1Floats + kT2Floats) * 4, kT2LBO, 128);
+      // staged Y (MN-major SWIZZLE_128B_BASE32B): both operands of the dW products
+      const uint64_t yh = make_desc(smem_u32(S.y_hi), kYLBO, kYSBO, 1), yl = make_desc(smem_u32(S.y_lo), kYLBO, kYSBO, 1);
       constexpr uint32_t id_fwd = make_idesc_ex(kN, 0, 0);
-      constexpr uint32_t id_dx2 = make_idesc_ex(48, 0, 1), id_dx1 = make_idesc_ex(32, 0, 1);
+      constexpr uint32_t id_dx2 = make_idesc_ex(48, 0, 0), id_dx1 = make_idesc_ex(32, 0, 0);
       constexpr uint32_t id_dw2 = make_idesc_ex(48, 1, 1), id_dw1 = make_idesc_ex(32, 1, 1);
       constexpr uint64_t kFwdStep = (2 * kLBO) >> 4;      // K-major: 8 k = two 16-byte chunks
-      constexpr uint64_t kTrStep = kSBO >> 4;             // transposed view: 8 gates = one n/8 group
-      constexpr uint64_t kDzStep = kDzKBlock >> 4, kXStep = kXKBlock >> 4;
+      constexpr uint64_t kT1Step = (2 * kT1LBO) >> 4, kT2Step = (2 * kT2LBO) >> 4;  // 8 gates = two 16-byte chunks
+      constexpr uint64_t kYStep = (2 * kYSBO) >> 4;       // 8 coordinates = two K atoms
       const uint32_t tD1 = tmem_base + cD1, tD2 = tmem_base + cD2, tAFh = tmem_base + cAFh, tAFl = tmem_base + cAFl;
       const uint32_t tAZh = tmem_base + cAZh, tAZl = tmem_base + cAZl, tW2 = tmem_base + cW2, tW1 = tmem_base + cW1;
       uint32_t pa = 0;
@@ -457,29 +461,29 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
           // dX2 = dZ2 . W2^T   and   dW2^T += dZ2^T . X2
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
           for (int kc = 0; kc < kN / 8; ++kc) {
-            mma_tf32_ts(tD2, tAZl + 8 * kc, t2h + kc * kTrStep, id_dx2, kc > 0 ? 1u : 0u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t2l + kc * kTrStep, id_dx2, 1u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t2h + kc * kTrStep, id_dx2, 1u);
+            mma_tf32_ts(tD2, tAZl + 8 * kc, t2h + kc * kT2Step, id_dx2, kc > 0 ? 1u : 0u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t2l + kc * kT2Step, id_dx2, 1u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t2h + kc * kT2Step, id_dx2, 1u);
           }
           tc_commit(&S.d_ready);
           for (int kb = 0; kb < 16; ++kb) {
-            mma_tf32_ss(tW2, dzl + kb * kDzStep, xh + kb * kXStep, id_dw2, 1u);
-            mma_tf32_ss(tW2, dzh + kb * kDzStep, xl + kb * kXStep, id_dw2, 1u);
-            mma_tf32_ss(tW2, dzh + kb * kDzStep, xh + kb * kXStep, id_dw2, 1u);
+            mma_tf32_ss(tW2, yl + kb * kYStep, yh + kb * kYStep, id_dw2, 1u);
+            mma_tf32_ss(tW2, yh + kb * kYStep, yl + kb * kYStep, id_dw2, 1u);
+            mma_tf32_ss(tW2, yh + kb * kYStep, yh + kb * kYStep, id_dw2, 1u);
           }
           tc_commit(&S.w_done);
           // dX1 = dZ1 . W1^T   and   dW1^T += dZ1^T . X1
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
           for (int kc = 0; kc < kN / 8; ++kc) {
-            mma_tf32_ts(tD2, tAZl + 8 * kc, t1h + kc * kTrStep, id_dx1, kc > 0 ? 1u : 0u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t1l + kc * kTrStep, id_dx1, 1u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t1h + kc * kTrStep, id_dx1, 1u);
+            mma_tf32_ts(tD2, tAZl + 8 * kc, t1h + kc * kT1Step, id_dx1, kc > 0 ? 1u : 0u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t1l + kc * kT1Step, id_dx1, 1u);
+            mma_tf32_ts(tD2, tAZh + 8 * kc, t1h + kc * kT1Step, id_dx1, 1u);
           }
           tc_commit(&S.d_ready);
           for (int kb = 0; kb < 16; ++kb) {
-            mma_tf32_ss(tW1, dzl + kb * kDzStep, xh + kb * kXStep, id_dw1, 1u);
-            mma_tf32_ss(tW1, dzh + kb * kDzStep, xl + kb * kXStep, id_dw1, 1u);
-            mma_tf32_ss(tW1, dzh + kb * kDzStep, xh + kb * kXStep, id_dw1, 1u);
+            mma_tf32_ss(tW1, yl + kb * kYStep, yh + kb * kYStep, id_dw1, 1u);
+            mma_tf32_ss(tW1, yh + kb * kYStep, yl + kb * kYStep, id_dw1, 1u);
+            mma_tf32_ss(tW1, yh + kb * kYStep, yh + kb * kYStep, id_dw1, 1u);
           }
           tc_commit(&S.w_done);
         }
@@ -497,9 +501,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
 
 template <class C>
 int tc_launch_bwd(const NetRt& rt, const l2o_bwd_args& a, float* img, cudaStream_t st, int sms) {
-  tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img);
+  tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 1);
   auto k = tcb::unroll_bwd_kernel<C>;
-  const size_t smem = sizeof(tcb::SmemB) + 128;
+  const size_t smem = sizeof(tcb::SmemB) + 1024;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
   const int64_t ntiles = (a.n + 127) / 128;
   const int grid = (int)(ntiles < sms ? ntiles : sms);

@@ -144,7 +144,11 @@ int l2o_unroll_bwd(l2o_handle h, const l2o_bwd_args* a, void* stream) {
   if (h->state_floats > 0 && !a->ckpt) return L2O_E_INVALID;
   if (!a->g_rec && (!a->labels || a->n_total <= 0)) return L2O_E_INVALID;
   if (a->n == 0 || a->T == 0) return L2O_OK;
-  return l2o::ffma_unroll_bwd(h, *a, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_can = l2o::tc_bwd_ok(h, *a);
+  if (h->engine == L2O_ENGINE_TC) return tc_can ? l2o::tc_unroll_bwd(h, *a, st) : L2O_E_UNSUPPORTED;
+  if (h->engine == L2O_ENGINE_AUTO && tc_can && l2o::tc_bwd_auto_default()) return l2o::tc_unroll_bwd(h, *a, st);
+  return l2o::ffma_unroll_bwd(h, *a, st);
 }
 
 int l2o_adam_step(float* theta, const double* dtheta, float* m, float* v, int64_t n, int32_t k, float lr, float beta1,

@@ -38,7 +38,10 @@ int ffma_unroll_bwd(const l2o_net* h, const l2o_bwd_args& a, cudaStream_t st);
 bool tc_supported(int cfg);
 bool tc_fwd_ok(const l2o_unroll_args& a);
 int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st);
-bool tc_auto_default();  // does ENGINE_AUTO pick the tcgen05 engine when it can?
+bool tc_auto_default();
+bool tc_bwd_auto_default();
+bool tc_bwd_ok(const l2o_net* h, const l2o_bwd_args& a);
+int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st);  // does ENGINE_AUTO pick the tcgen05 engine when it can?
 }  // namespace l2o
 
 #define L2O_CUDA_TRY(expr)                                              \

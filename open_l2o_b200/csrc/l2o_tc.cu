@@ -1,22 +1,50 @@
 // tcgen05 engine translation unit.
 #include "cwlstm_ffma.cuh"   // load_vec / store_vec / preprocess helpers
 #include "cwlstm_tc.cuh"
+#include "cwlstm_tc_bwd.cuh"
 #include "l2o_internal.h"
 
 namespace l2o {
 bool tc_supported(int cfg) { return cfg == 0 || cfg == 1; }  // LSTM-20x2 with identity / LogAndSign preprocessing
 bool tc_fwd_ok(const l2o_unroll_args& a) { return a.m == nullptr && a.feat_rec == nullptr; }
-bool tc_auto_default() { return true; }  // parity-green on the B200 (tests/test_tc_gpu.py): AUTO prefers tcgen05
+bool tc_auto_default() { return true; }
+bool tc_bwd_auto_default() { return true; }  // parity-green on the B200 (tests/test_tc_gpu.py)
 
-int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st) {
-  if (!tc_supported(h->cfg) || !tc_fwd_ok(a)) return L2O_E_UNSUPPORTED;
+static int ensure_image(l2o_net* h) {
   int dev = 0;
   L2O_CUDA_TRY(cudaGetDevice(&dev));
   if (h->tc_img == nullptr || h->tc_img_dev != dev) {
     if (h->tc_img) cudaFree(h->tc_img);
     h->tc_img = nullptr;
-    L2O_CUDA_TRY(cudaMalloc(&h->tc_img, tc::kImgBytes));
+    L2O_CUDA_TRY(cudaMalloc(&h->tc_img, tc::kImgAllBytes));
     h->tc_img_dev = dev;
+  }
+  return L2O_OK;
+}
+
+bool tc_bwd_ok(const l2o_net* h, const l2o_bwd_args& a) {
+  return tc_supported(h->cfg) && a.g_rec != nullptr && a.labels == nullptr && !h->rt.tanh_output;
+}
+
+int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {
+  if (!tc_bwd_ok(h, a)) return L2O_E_UNSUPPORTED;
+  int rc = ensure_image(h);
+  if (rc) return rc;
+  const int sms = device_sms();
+  if (sms <= 0) return L2O_E_CUDA;
+  rc = L2O_E_UNSUPPORTED;
+  if (h->cfg == 0) rc = tc_launch_bwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+  if (h->cfg == 1) rc = tc_launch_bwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+  if (rc == L2O_OK) count_launch(2);
+  if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_unroll_bwd launch");
+  return rc;
+}
+
+int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st) {
+  if (!tc_supported(h->cfg) || !tc_fwd_ok(a)) return L2O_E_UNSUPPORTED;
+  {
+    int rc0 = ensure_image(h);
+    if (rc0) return rc0;
   }
   const int sms = device_sms();
   if (sms <= 0) return L2O_E_CUDA;

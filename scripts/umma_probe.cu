@@ -1,0 +1,103 @@
+// UMMA operand-addressing probe: D = A . B^T with B one-hot (float index jb) and A[i] = i+1 (tf32-exact for i < 2048).
+// For each jb the kernel reports, per D row m, the column that became non-zero and its value (= A float index + 1),
+// which reveals the hardware's (m, n, k) -> shared-memory address map for the given descriptors.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "cwlstm_ffma.cuh"
+#include "cwlstm_tc_bwd.cuh"
+using namespace l2o;
+using namespace l2o::tc;
+using namespace l2o::tcb;
+
+struct Params { int a_mn, b_mn, n; uint32_t lbo_a, sbo_a, lbo_b, sbo_b; int njb; int a_tmem; int ltype; };
+__device__ __forceinline__ uint64_t make_desc_lt(uint32_t saddr, uint32_t lbo, uint32_t sbo, int lt) { return make_desc(saddr, lbo, sbo) | ((uint64_t)lt << 61); }
+
+__global__ void __launch_bounds__(160, 1) probe(Params p, int* out_col, float* out_val) {
+  extern __shared__ __align__(1024) unsigned char raw[];
+  float* sa = reinterpret_cast<float*>(raw);            // 2048 floats
+  float* sb = sa + 2048;                                // 2048 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 2048);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) { sa[i] = (float)(i + 1); sb[i] = 0.f; }
+  if (warp == 4) {
+    if (lane == 0) { mbar_init(&bars[0], 128); mbar_init(&bars[1], 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *slot;
+  uint32_t pa = 0, pd = 0;
+  for (int jb = 0; jb < p.njb; ++jb) {
+    if (warp < 4) {
+      if (threadIdx.x == 0) { if (jb > 0) sb[jb - 1] = 0.f; sb[jb] = 1.0f; }
+      if (p.a_tmem) {  // A from TMEM: lane = m, 8 columns k ; value = 1 + m*8 + k
+        const int m = warp * 32 + lane;
+        const uint32_t ta = tb + ((uint32_t)(warp * 32) << 16) + 256;
+        tmem_st4(ta, 1.f + m * 8, 2.f + m * 8, 3.f + m * 8, 4.f + m * 8);
+        tmem_st4(ta + 4, 5.f + m * 8, 6.f + m * 8, 7.f + m * 8, 8.f + m * 8);
+        tc_wait_st();
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&bars[0]);
+      mbar_wait(&bars[1], pd); pd ^= 1;
+      tc_fence_after();
+      const int m = warp * 32 + lane;
+      const uint32_t td = tb + ((uint32_t)(warp * 32) << 16);
+      int col = -1; float val = 0.f; int nnz = 0;
+      for (int c4 = 0; c4 < p.n / 4; ++c4) {
+        float v[4];
+        tmem_ld4(td + 4 * c4, v);
+        for (int e = 0; e < 4; ++e) if (v[e] != 0.f) { col = 4 * c4 + e; val = v[e]; ++nnz; }
+      }
+      out_col[jb * 128 + m] = nnz == 1 ? col : (nnz == 0 ? -1 : -100 - nnz);
+      out_val[jb * 128 + m] = val;
+      tc_fence_before();
+    } else if (lane == 0) {
+      mbar_wait(&bars[0], pa); pa ^= 1;
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_ex(p.n, p.a_mn, p.b_mn);
+      const uint64_t bd = make_desc_lt(smem_u32(sb), p.lbo_b, p.sbo_b, p.ltype);
+      if (p.a_tmem) mma_tf32_ts(tb, tb + 256, bd, idesc, 0u);
+      else mma_tf32_ss(tb, make_desc_lt(smem_u32(sa), p.lbo_a, p.sbo_a, p.ltype), bd, idesc, 0u);
+      tc_commit(&bars[1]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) tmem_dealloc(tb, 512);
+}
+
+int main(int argc, char** argv) {
+  Params p;
+  p.a_mn = atoi(argv[1]); p.b_mn = atoi(argv[2]); p.n = atoi(argv[3]);
+  p.lbo_a = atoi(argv[4]); p.sbo_a = atoi(argv[5]); p.lbo_b = atoi(argv[6]); p.sbo_b = atoi(argv[7]);
+  p.njb = atoi(argv[8]); p.a_tmem = atoi(argv[9]); p.ltype = argc > 10 ? atoi(argv[10]) : 0;
+  int* dcol; float* dval;
+  cudaMalloc(&dcol, p.njb * 128 * sizeof(int)); cudaMalloc(&dval, p.njb * 128 * sizeof(float));
+  const size_t smem = 4096 * 4 + 64;
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe<<<1, 160, smem>>>(p, dcol, dval);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+  std::vector<int> col(p.njb * 128); std::vector<float> val(p.njb * 128);
+  cudaMemcpy(col.data(), dcol, col.size() * 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(val.data(), dval, val.size() * 4, cudaMemcpyDeviceToHost);
+  printf("# a_mn=%d b_mn=%d N=%d lbo_a=%u sbo_a=%u lbo_b=%u sbo_b=%u a_tmem=%d\n", p.a_mn, p.b_mn, p.n, p.lbo_a, p.sbo_a, p.lbo_b, p.sbo_b, p.a_tmem);
+  for (int jb = 0; jb < p.njb; ++jb) {
+    // B float index jb -> column n ; A index (value-1) for m = 0,1,2,3,4,8,127
+    if (col[jb * 128] == -1 && argc > 11) continue;
+    printf("jb=%4d n=%3d | A idx m0=%4d m1=%4d m3=%4d m4=%4d m8=%4d m9=%4d m16=%4d m31=%4d m32=%4d m40=%4d m64=%4d m127=%4d\n", jb, col[jb * 128],
+           (int)val[jb * 128 + 0] - 1, (int)val[jb * 128 + 1] - 1, (int)val[jb * 128 + 3] - 1, (int)val[jb * 128 + 4] - 1,
+           (int)val[jb * 128 + 8] - 1, (int)val[jb * 128 + 9] - 1, (int)val[jb * 128 + 16] - 1, (int)val[jb * 128 + 31] - 1,
+           (int)val[jb * 128 + 32] - 1, (int)val[jb * 128 + 40] - 1, (int)val[jb * 128 + 64] - 1, (int)val[jb * 128 + 127] - 1);
+  }
+  return 0;
+}

@@ -85,3 +85,32 @@ def test_tc_matches_ffma_engine_large():
         outs[eng] = (x, arena, fx, g_rec)
     for u, v in zip(outs[ENGINE_TC], outs[ENGINE_FFMA]):
         assert rel_err(u, v) <= REL_TOL
+
+
+@pytest.mark.parametrize("name", ["dm_identity", "dm_logsign"])
+def test_tc_bwd_matches_ffma_bwd(name):
+    """Same checkpoints / recorded gradients through both BPTT kernels (multi-tile, ragged tail)."""
+    from open_l2o_b200.engine import ENGINE_FFMA, ENGINE_TC
+    spec = SPECS[name]
+    n, T = 148 * 128 + 77, 5
+    gen = torch.Generator().manual_seed(21)
+    theta = _theta(spec, gain=0.05).to(DEV)
+    from tests.helpers import wild_gradients
+    if spec.preprocess_name == "LogAndSign":
+        g_rec = torch.stack([wild_gradients(n, gen) for _ in range(T + 1)]).to(DEV)
+    else:
+        g_rec = (torch.randn(T + 1, n, generator=gen) * 0.5).to(DEV)
+    h = make_handle(spec)
+    h.set_engine(ENGINE_FFMA)
+    sf = h.state_floats
+    arena = h.new_state(n, DEV)
+    ckpt = torch.zeros((T + 1) * sf * n, device=DEV)
+    h.unroll_fwd(theta, n, T, arena, in_seq=g_rec[:T].contiguous(), ckpt=ckpt)
+    outs = {}
+    for eng in (ENGINE_FFMA, ENGINE_TC):
+        h.set_engine(eng)
+        d = torch.zeros(h.n_theta, dtype=torch.float64, device=DEV)
+        h.unroll_bwd(theta, n, T, g_rec[:T].contiguous(), ckpt, d, g_rec=g_rec)
+        torch.cuda.synchronize()
+        outs[eng] = d
+    assert rel_err(outs[ENGINE_TC], outs[ENGINE_FFMA]) <= REL_TOL
