@@ -88,6 +88,19 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
+// warp-uniform leader election: the whole warp runs the issuing code (operands stay in uniform registers),
+// only the elected lane's tcgen05.mma / commit takes effect
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -433,43 +446,52 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
     }
   } else {
     // =============================== MMA issuer warp ===============================
+    // The whole warp runs this loop (warp-uniform => descriptors live in uniform registers and the UTCHMMA issue
+    // rate matches the tensor pipe); elect.sync picks the one lane whose tcgen05.mma / commit take effect.
     mbar_wait(&S.wbar, 0);  // weights landed (TMA complete_tx)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kN);
-      const uint32_t img_s = smem_u32(S.img);
-      const uint64_t b1h = make_bdesc(img_s);
-      const uint64_t b1l = make_bdesc(img_s + kB1Floats * 4);
-      const uint64_t b2h = make_bdesc(img_s + 2 * kB1Floats * 4);
-      const uint64_t b2l = make_bdesc(img_s + (2 * kB1Floats + kB2Floats) * 4);
-      constexpr uint64_t kStep = (2 * kLBO) >> 4;  // descriptor start-address increment per K=8 chunk
-      uint32_t pa[kTiles] = {0, 0};
-      for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        for (int t = 0; t < T; ++t) {
+    const uint32_t idesc = make_idesc(kN);
+    const uint32_t img_s = smem_u32(S.img);
+    const uint64_t b1h = make_bdesc(img_s);
+    const uint64_t b1l = make_bdesc(img_s + kB1Floats * 4);
+    const uint64_t b2h = make_bdesc(img_s + 2 * kB1Floats * 4);
+    const uint64_t b2l = make_bdesc(img_s + (2 * kB1Floats + kB2Floats) * 4);
+    constexpr uint64_t kStep = (2 * kLBO) >> 4;  // descriptor start-address increment per K=8 chunk
+    uint32_t pa[kTiles] = {0, 0};
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      for (int t = 0; t < T; ++t) {
 #pragma unroll
-          for (int layer = 0; layer < 2; ++layer) {
+        for (int layer = 0; layer < 2; ++layer) {
 #pragma unroll
-            for (int tile = 0; tile < kTiles; ++tile) {
-              const uint32_t t_d = tmem_base + tile * kTileCols;
-              const uint32_t t_ah = t_d + kN;
-              const uint32_t t_al = t_ah + kACols;
-              mbar_wait(&S.a_ready[tile], pa[tile]);
-              pa[tile] ^= 1;
-              tc_fence_after();
-              const int nchunks = (layer == 0 ? kK1 : kK2) / 8;
-              const uint64_t bh = layer == 0 ? b1h : b2h;
-              const uint64_t bl = layer == 0 ? b1l : b2l;
-              for (int kc = 0; kc < nchunks; ++kc) {
-                mma_tf32_ts(t_d, t_al + 8 * kc, bh + kc * kStep, idesc, kc > 0 ? 1u : 0u);
-                mma_tf32_ts(t_d, t_ah + 8 * kc, bl + kc * kStep, idesc, 1u);
-                mma_tf32_ts(t_d, t_ah + 8 * kc, bh + kc * kStep, idesc, 1u);
+          for (int tile = 0; tile < kTiles; ++tile) {
+            const uint32_t t_d = tmem_base + tile * kTileCols;
+            const uint32_t t_ah = t_d + kN;
+            const uint32_t t_al = t_ah + kACols;
+            mbar_wait(&S.a_ready[tile], pa[tile]);
+            pa[tile] ^= 1;
+            tc_fence_after();
+            if (elect_one()) {
+              if (layer == 0) {
+#pragma unroll
+                for (int kc = 0; kc < kK1 / 8; ++kc) {
+                  mma_tf32_ts(t_d, t_al + 8 * kc, b1h + kc * kStep, idesc, kc > 0 ? 1u : 0u);
+                  mma_tf32_ts(t_d, t_ah + 8 * kc, b1l + kc * kStep, idesc, 1u);
+                  mma_tf32_ts(t_d, t_ah + 8 * kc, b1h + kc * kStep, idesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int kc = 0; kc < kK2 / 8; ++kc) {
+                  mma_tf32_ts(t_d, t_al + 8 * kc, b2h + kc * kStep, idesc, kc > 0 ? 1u : 0u);
+                  mma_tf32_ts(t_d, t_ah + 8 * kc, b2l + kc * kStep, idesc, 1u);
+                  mma_tf32_ts(t_d, t_ah + 8 * kc, b2h + kc * kStep, idesc, 1u);
+                }
               }
               tc_commit(&S.d_ready[tile]);
             }
+            __syncwarp();
           }
         }
       }
     }
-    __syncwarp();
   }
   // ---- teardown ----
   tc_fence_before();

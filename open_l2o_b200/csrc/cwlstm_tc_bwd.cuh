@@ -37,6 +37,15 @@ constexpr uint32_t kYLBO = 512;                  // bytes between 32-slot MN ato
 constexpr uint32_t kYSBO = 4 * 512;              // bytes between 4-coordinate K atoms
 constexpr int kYFloats = 128 * kYSlots;          // 16384 floats = 64 KB per hi / lo buffer
 
+#ifdef L2O_TC_PROF
+// timeline instrumentation (scripts/tc_bwd_prof.cu only): clock64 stamps of CTA 0 at every phase boundary
+__device__ long long g_prof[3 * 2048];
+#define L2O_PROF(role, idx) \
+  do { if (blockIdx.x == 0 && (idx) < 2048) g_prof[(role) * 2048 + (idx)] = clock64(); } while (0)
+#else
+#define L2O_PROF(role, idx) do { } while (0)
+#endif
+
 struct SmemB {
   float y_hi[kYFloats];        // 1024-B aligned (first member)
   float y_lo[kYFloats];
@@ -143,6 +152,9 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
   const int64_t slot = n * C::SF;
   const int64_t ntiles = (n + 127) / 128;
   uint32_t pd = 0;
+  int pi = 0;  // profile event index
+  const bool prof = (q == 0 && lane == 0);
+  (void)pi; (void)prof;
   // w_done completes exactly twice per step: dW2 (even completion, parity 0) then dW1 (odd, parity 1)
   float acc_wo[NU], acc_bo = 0.f;
 #pragma unroll
@@ -176,35 +188,43 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
         for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
         u4[C::F] = 1.0f;
       }
-      float h2p[NU];
+      float h2p[NU], c1p[NU], c2p[NU];
       {
         float h1p[NU];
 #pragma unroll
-        for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h2p[k] = 0.f; }
-        if (act) {
+        for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h2p[k] = 0.f; c1p[k] = 0.f; c2p[k] = 0.f; }
+        if (act) {  // all four checkpoint rows at once: one exposed DRAM latency per step
           load_vec<NU>(ck + i * kH + U0, h1p);
           load_vec<NU>(ck + 2 * n * kH + i * kH + U0, h2p);
+          load_vec<NU>(ck + (n + i) * kH + U0, c1p);
+          load_vec<NU>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
+          if (t > 0) {  // pull the next step's rows towards L2 while this step computes
+            const float* nk = ck - slot;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + U0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + U0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + U0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
+          }
         }
-        if (HALF == 0) put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
+        if (HALF == 1) put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
           put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
           put4(tAFh, tAFl, kColH2 + U0 + 4 * g4, h2p + 4 * g4, nullptr, nullptr, 0, true, false);
         }
       }
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready);
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       // ---------------- P1: h1n = LSTM1 forward (only what layer 2 needs) ----------------
       float h1n[NU];
       mbar_wait(&S.d_ready, pd);
       pd ^= 1;
       tc_fence_after();
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       {
-        float c1p[NU];
-#pragma unroll
-        for (int k = 0; k < NU; ++k) c1p[k] = 0.f;
-        if (act) load_vec<NU>(ck + (n + i) * kH + U0, c1p);
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
           float z[16], g[16];
@@ -221,19 +241,19 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready);
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       // ---------------- P2: layer-2 forward recompute + output layer + layer-2 backward ----------------
       mbar_wait(&S.d_ready, pd);
       pd ^= 1;
       tc_fence_after();
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
+
       const float dy = rt.scale * lam;  // dDelta_t = sum_{tau>t} g_tau ; linear output (tanh_output handled by FFMA engine)
-      if (HALF == 0) acc_bo += dy;
+      if (HALF == 1) acc_bo += dy;
       // staging buffers must be free: the dW1 MMAs of the previous step have completed
       mbar_wait(&S.w_done, 1);  // passes trivially on the fresh barrier (first step)
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       {
-        float c2p[NU];
-#pragma unroll
-        for (int k = 0; k < NU; ++k) c2p[k] = 0.f;
-        if (act) load_vec<NU>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
           float z[16], g[16];
@@ -253,7 +273,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
           }
         }
         // X2 row = [0.. 1 .. | h1n | h2p]
-        if (HALF == 0) {
+        if (HALF == 1) {
           float x0[4] = {0.f, 0.f, 0.f, 0.f};
           x0[C::F] = 1.0f;
           put4(0, 0, 0, x0, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
@@ -268,10 +288,13 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready);
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       // ---------------- P3: layer-1 backward ----------------
       mbar_wait(&S.d_ready, pd);
       pd ^= 1;
       tc_fence_after();
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
+
       float dh1[NU];
 #pragma unroll
       for (int g4 = 0; g4 < NU / 4; ++g4) {
@@ -284,14 +307,12 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
         for (int u = 0; u < 4; ++u) dh2c[4 * g4 + u] = v[u];
       }
       mbar_wait(&S.w_done, 0);  // dW2 MMAs done: staging may be overwritten
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       {
-        float c1p[NU], h1p[NU];
+        float h1p[NU];
 #pragma unroll
-        for (int k = 0; k < NU; ++k) { c1p[k] = 0.f; h1p[k] = 0.f; }
-        if (act) {
-          load_vec<NU>(ck + (n + i) * kH + U0, c1p);
-          load_vec<NU>(ck + i * kH + U0, h1p);
-        }
+        for (int k = 0; k < NU; ++k) h1p[k] = 0.f;
+        if (act) load_vec<NU>(ck + i * kH + U0, h1p);  // re-read (cache hit): cheaper than 12 live registers
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
           float z[16], g[16];
@@ -307,16 +328,19 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
           }
           put4(0, 0, 0, h1p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
         }
-        if (HALF == 0) put4(0, 0, 0, u4, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
+        if (HALF == 1) put4(0, 0, 0, u4, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
       }
       fence_proxy_async();
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready);
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       // ---------------- P4: carry for step t-1 ----------------
       mbar_wait(&S.d_ready, pd);
       pd ^= 1;
       tc_fence_after();
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
+
 #pragma unroll
       for (int g4 = 0; g4 < NU / 4; ++g4) {
         float v[4];
@@ -335,7 +359,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) atomicAdd(&a.dtheta[C::O_WO + U0 + k], (double)v);
   }
-  if (HALF == 0) {
+  if (HALF == 1) {
     float v = acc_bo;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -418,7 +442,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
     else epilogue<C, 1>(a, rt, S, tmem_base, warp, lane);
   } else {
     mbar_wait(&S.wbar, 0);
-    if (lane == 0) {
+    {  // warp-uniform issuer (see cwlstm_tc.cuh): elect.sync predicates the MMAs / commits to one lane
       const uint32_t img_s = smem_u32(S.img);
       // forward (K-major) views
       const uint64_t b1h = make_bdesc(img_s), b1l = make_bdesc(img_s + kB1Floats * 4);
@@ -440,52 +464,88 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
       const uint32_t tD1 = tmem_base + cD1, tD2 = tmem_base + cD2, tAFh = tmem_base + cAFh, tAFl = tmem_base + cAFl;
       const uint32_t tAZh = tmem_base + cAZh, tAZl = tmem_base + cAZl, tW2 = tmem_base + cW2, tW1 = tmem_base + cW1;
       uint32_t pa = 0;
+      int pi = 0;
+      (void)pi;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int t = T - 1; t >= 0; --t) {
           // Z1
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
-          for (int kc = 0; kc < kK1 / 8; ++kc) {
-            mma_tf32_ts(tD1, tAFl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
-            mma_tf32_ts(tD1, tAFh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
-            mma_tf32_ts(tD1, tAFh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
+          L2O_PROF(2, pi); ++pi;
+          if (elect_one()) {
+#pragma unroll
+            for (int kc = 0; kc < kK1 / 8; ++kc) {
+              mma_tf32_ts(tD1, tAFl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+              mma_tf32_ts(tD1, tAFh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
+              mma_tf32_ts(tD1, tAFh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
+            }
+            tc_commit(&S.d_ready);
           }
-          tc_commit(&S.d_ready);
+          __syncwarp();
+          L2O_PROF(2, pi); ++pi;
           // Z2
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
-          for (int kc = 0; kc < kK2 / 8; ++kc) {
-            mma_tf32_ts(tD2, tAFl + 8 * kc, b2h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
-            mma_tf32_ts(tD2, tAFh + 8 * kc, b2l + kc * kFwdStep, id_fwd, 1u);
-            mma_tf32_ts(tD2, tAFh + 8 * kc, b2h + kc * kFwdStep, id_fwd, 1u);
+          L2O_PROF(2, pi); ++pi;
+          if (elect_one()) {
+#pragma unroll
+            for (int kc = 0; kc < kK2 / 8; ++kc) {
+              mma_tf32_ts(tD2, tAFl + 8 * kc, b2h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+              mma_tf32_ts(tD2, tAFh + 8 * kc, b2l + kc * kFwdStep, id_fwd, 1u);
+              mma_tf32_ts(tD2, tAFh + 8 * kc, b2h + kc * kFwdStep, id_fwd, 1u);
+            }
+            tc_commit(&S.d_ready);
           }
-          tc_commit(&S.d_ready);
+          __syncwarp();
+          L2O_PROF(2, pi); ++pi;
           // dX2 = dZ2 . W2^T   and   dW2^T += dZ2^T . X2
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
-          for (int kc = 0; kc < kN / 8; ++kc) {
-            mma_tf32_ts(tD2, tAZl + 8 * kc, t2h + kc * kT2Step, id_dx2, kc > 0 ? 1u : 0u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t2l + kc * kT2Step, id_dx2, 1u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t2h + kc * kT2Step, id_dx2, 1u);
+          L2O_PROF(2, pi); ++pi;
+          if (elect_one()) {
+#pragma unroll
+            for (int kc = 0; kc < kN / 8; ++kc) {
+              mma_tf32_ts(tD2, tAZl + 8 * kc, t2h + kc * kT2Step, id_dx2, kc > 0 ? 1u : 0u);
+              mma_tf32_ts(tD2, tAZh + 8 * kc, t2l + kc * kT2Step, id_dx2, 1u);
+              mma_tf32_ts(tD2, tAZh + 8 * kc, t2h + kc * kT2Step, id_dx2, 1u);
+            }
+            tc_commit(&S.d_ready);
           }
-          tc_commit(&S.d_ready);
-          for (int kb = 0; kb < 16; ++kb) {
-            mma_tf32_ss(tW2, yl + kb * kYStep, yh + kb * kYStep, id_dw2, 1u);
-            mma_tf32_ss(tW2, yh + kb * kYStep, yl + kb * kYStep, id_dw2, 1u);
-            mma_tf32_ss(tW2, yh + kb * kYStep, yh + kb * kYStep, id_dw2, 1u);
+          __syncwarp();
+          L2O_PROF(2, pi); ++pi;
+          if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < 16; ++kb) {
+              mma_tf32_ss(tW2, yl + kb * kYStep, yh + kb * kYStep, id_dw2, 1u);
+              mma_tf32_ss(tW2, yh + kb * kYStep, yl + kb * kYStep, id_dw2, 1u);
+              mma_tf32_ss(tW2, yh + kb * kYStep, yh + kb * kYStep, id_dw2, 1u);
+            }
+            tc_commit(&S.w_done);
           }
-          tc_commit(&S.w_done);
+          __syncwarp();
+          L2O_PROF(2, pi); ++pi;
           // dX1 = dZ1 . W1^T   and   dW1^T += dZ1^T . X1
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
-          for (int kc = 0; kc < kN / 8; ++kc) {
-            mma_tf32_ts(tD2, tAZl + 8 * kc, t1h + kc * kT1Step, id_dx1, kc > 0 ? 1u : 0u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t1l + kc * kT1Step, id_dx1, 1u);
-            mma_tf32_ts(tD2, tAZh + 8 * kc, t1h + kc * kT1Step, id_dx1, 1u);
+          L2O_PROF(2, pi); ++pi;
+          if (elect_one()) {
+#pragma unroll
+            for (int kc = 0; kc < kN / 8; ++kc) {
+              mma_tf32_ts(tD2, tAZl + 8 * kc, t1h + kc * kT1Step, id_dx1, kc > 0 ? 1u : 0u);
+              mma_tf32_ts(tD2, tAZh + 8 * kc, t1l + kc * kT1Step, id_dx1, 1u);
+              mma_tf32_ts(tD2, tAZh + 8 * kc, t1h + kc * kT1Step, id_dx1, 1u);
+            }
+            tc_commit(&S.d_ready);
           }
-          tc_commit(&S.d_ready);
-          for (int kb = 0; kb < 16; ++kb) {
-            mma_tf32_ss(tW1, yl + kb * kYStep, yh + kb * kYStep, id_dw1, 1u);
-            mma_tf32_ss(tW1, yh + kb * kYStep, yl + kb * kYStep, id_dw1, 1u);
-            mma_tf32_ss(tW1, yh + kb * kYStep, yh + kb * kYStep, id_dw1, 1u);
+          __syncwarp();
+          L2O_PROF(2, pi); ++pi;
+          if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < 16; ++kb) {
+              mma_tf32_ss(tW1, yl + kb * kYStep, yh + kb * kYStep, id_dw1, 1u);
+              mma_tf32_ss(tW1, yh + kb * kYStep, yl + kb * kYStep, id_dw1, 1u);
+              mma_tf32_ss(tW1, yh + kb * kYStep, yh + kb * kYStep, id_dw1, 1u);
+            }
+            tc_commit(&S.w_done);
           }
-          tc_commit(&S.w_done);
+          __syncwarp();
+          L2O_PROF(2, pi); ++pi;
         }
       }
     }

@@ -1,0 +1,49 @@
+// Timeline probe for the tcgen05 BPTT kernel: runs it on synthetic data with L2O_TC_PROF stamps and prints per-phase
+// durations (cycles) of CTA 0 for a few steps.  Debug tool; not part of the library.
+#define L2O_TC_PROF 1
+#include <cstdio>
+#include <vector>
+#include "cwlstm_ffma.cuh"
+#include "cwlstm_tc_bwd.cuh"
+using namespace l2o;
+int main() {
+  using C = Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>;
+  const int64_t n = 148 * 128 * 2; const int T = 8;
+  float *theta, *in_seq, *ckpt, *g_rec, *img; double* dth;
+  cudaMalloc(&theta, C::P * 4); cudaMalloc(&in_seq, (T + 1) * n * 4); cudaMalloc(&g_rec, (T + 1) * n * 4);
+  cudaMalloc(&ckpt, (size_t)(T + 1) * n * C::SF * 4); cudaMalloc(&dth, C::P * 8); cudaMalloc(&img, tc::kImgAllBytes);
+  std::vector<float> h(C::P); for (int i = 0; i < C::P; ++i) h[i] = 0.05f * ((i * 2654435761u % 1000) / 500.f - 1.f);
+  cudaMemcpy(theta, h.data(), C::P * 4, cudaMemcpyHostToDevice);
+  cudaMemset(in_seq, 0, (T + 1) * n * 4); cudaMemset(g_rec, 0, (T + 1) * n * 4);
+  cudaMemset(ckpt, 0, (size_t)(T + 1) * n * C::SF * 4); cudaMemset(dth, 0, C::P * 8);
+  l2o_bwd_args a{}; a.n = n; a.T = T; a.theta = theta; a.in_seq = in_seq; a.ckpt = ckpt; a.g_rec = g_rec; a.dtheta = dth;
+  NetRt rt{1.f, 0.f, 1.f, 0};
+  for (int rep = 0; rep < 2; ++rep) {
+    int rc = tc_launch_bwd<C>(rt, a, img, 0, 148);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc || e != cudaSuccess) { printf("rc=%d err=%s\n", rc, cudaGetErrorString(e)); return 1; }
+  }
+  std::vector<long long> p(3 * 2048);
+  cudaMemcpyFromSymbol(p.data(), tcb::g_prof, sizeof(long long) * 3 * 2048);
+  const char* en[12] = {"P0 done(loads+A_F st)", "arrived", "Z1 ready", "P1 arrived", "Z2 ready", "w_done(dW1 prev)", "P2 arrived", "dX2 ready",
+                        "w_done(dW2)", "P3 arrived", "dX1 ready", ""};
+  for (int role = 0; role < 2; ++role) {
+    printf("== epilogue half %d (warp q=0 lane 0): cycles since previous event, steps 2..5 of tile 0\n", role);
+    for (int st = 2; st < 6; ++st) {
+      printf(" step %d:", st);
+      for (int e = 0; e < 11; ++e) {
+        const int idx = st * 11 + e;
+        printf(" %s=%lld", en[e], p[role * 2048 + idx] - p[role * 2048 + idx - 1]);
+      }
+      printf("  | step total %lld\n", p[role * 2048 + st * 11 + 10] - p[role * 2048 + (st - 1) * 11 + 10]);
+    }
+  }
+  const char* in[10] = {"a_ready(P0)", "Z1 issued", "a_ready(P1)", "Z2 issued", "a_ready(P2)", "dX2 issued", "dW2 issued", "a_ready(P3)", "dX1 issued", "dW1 issued"};
+  printf("== issuer: cycles since previous event\n");
+  for (int st = 2; st < 6; ++st) {
+    printf(" step %d:", st);
+    for (int e = 0; e < 10; ++e) { const int idx = st * 10 + e; printf(" %s=%lld", in[e], p[2 * 2048 + idx] - p[2 * 2048 + idx - 1]); }
+    printf("\n");
+  }
+  return 0;
+}

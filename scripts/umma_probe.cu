@@ -10,7 +10,7 @@ using namespace l2o;
 using namespace l2o::tc;
 using namespace l2o::tcb;
 
-struct Params { int a_mn, b_mn, n; uint32_t lbo_a, sbo_a, lbo_b, sbo_b; int njb; int a_tmem; int ltype; };
+struct Params { int a_mn, b_mn, n; uint32_t lbo_a, sbo_a, lbo_b, sbo_b; int njb; int a_tmem; int ltype; int reps; };
 __device__ __forceinline__ uint64_t make_desc_lt(uint32_t saddr, uint32_t lbo, uint32_t sbo, int lt) { return make_desc(saddr, lbo, sbo) | ((uint64_t)lt << 61); }
 
 __global__ void __launch_bounds__(160, 1) probe(Params p, int* out_col, float* out_val) {
@@ -18,11 +18,11 @@ __global__ void __launch_bounds__(160, 1) probe(Params p, int* out_col, float* o
   float* sa = reinterpret_cast<float*>(raw);            // 2048 floats
   float* sb = sa + 2048;                                // 2048 floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 2048);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 3);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) { sa[i] = (float)(i + 1); sb[i] = 0.f; }
   if (warp == 4) {
-    if (lane == 0) { mbar_init(&bars[0], 128); mbar_init(&bars[1], 1); fence_barrier_init(); }
+    if (lane == 0) { mbar_init(&bars[0], 128); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); fence_barrier_init(); }
     __syncwarp();
     tmem_alloc(slot, 512);
     tmem_relinquish();
@@ -59,14 +59,39 @@ __global__ void __launch_bounds__(160, 1) probe(Params p, int* out_col, float* o
       out_col[jb * 128 + m] = nnz == 1 ? col : (nnz == 0 ? -1 : -100 - nnz);
       out_val[jb * 128 + m] = val;
       tc_fence_before();
-    } else if (lane == 0) {
+    } else {
       mbar_wait(&bars[0], pa); pa ^= 1;
       tc_fence_after();
+      const bool leader = elect_one();
       const uint32_t idesc = make_idesc_ex(p.n, p.a_mn, p.b_mn);
       const uint64_t bd = make_desc_lt(smem_u32(sb), p.lbo_b, p.sbo_b, p.ltype);
-      if (p.a_tmem) mma_tf32_ts(tb, tb + 256, bd, idesc, 0u);
-      else mma_tf32_ss(tb, make_desc_lt(smem_u32(sa), p.lbo_a, p.sbo_a, p.ltype), bd, idesc, 0u);
-      tc_commit(&bars[1]);
+      const uint64_t ad = make_desc_lt(smem_u32(sa), p.lbo_a, p.sbo_a, p.ltype);
+      if (p.reps > 0 && jb == 0) {   // throughput: reps back-to-back MMAs, cycles from first issue to completion
+        const long long t0 = clock64();
+        for (int r = 0; r < p.reps; r += 8) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (leader) {
+              if (p.a_tmem) mma_tf32_ts(tb, tb + 256, bd, idesc, 1u);
+              else mma_tf32_ss(tb, ad, bd, idesc, 1u);
+            }
+          }
+        }
+        const long long t1 = clock64();
+        if (leader) tc_commit(&bars[2]);
+        mbar_wait(&bars[2], 0);
+        const long long t2 = clock64();
+        if (leader) {
+          out_val[p.njb * 128] = (float)(t1 - t0) / p.reps;
+          out_val[p.njb * 128 + 1] = (float)(t2 - t0) / p.reps;
+        }
+      }
+      if (leader) {
+        if (p.a_tmem) mma_tf32_ts(tb, tb + 256, bd, idesc, 0u);
+        else mma_tf32_ss(tb, ad, bd, idesc, 0u);
+        tc_commit(&bars[1]);
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -79,18 +104,19 @@ int main(int argc, char** argv) {
   Params p;
   p.a_mn = atoi(argv[1]); p.b_mn = atoi(argv[2]); p.n = atoi(argv[3]);
   p.lbo_a = atoi(argv[4]); p.sbo_a = atoi(argv[5]); p.lbo_b = atoi(argv[6]); p.sbo_b = atoi(argv[7]);
-  p.njb = atoi(argv[8]); p.a_tmem = atoi(argv[9]); p.ltype = argc > 10 ? atoi(argv[10]) : 0;
+  p.njb = atoi(argv[8]); p.a_tmem = atoi(argv[9]); p.ltype = argc > 10 ? atoi(argv[10]) : 0; p.reps = argc > 12 ? atoi(argv[12]) : 0;
   int* dcol; float* dval;
-  cudaMalloc(&dcol, p.njb * 128 * sizeof(int)); cudaMalloc(&dval, p.njb * 128 * sizeof(float));
-  const size_t smem = 4096 * 4 + 64;
+  cudaMalloc(&dcol, p.njb * 128 * sizeof(int)); cudaMalloc(&dval, (p.njb * 128 + 2) * sizeof(float));
+  const size_t smem = 4096 * 4 + 64 + 1024;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   probe<<<1, 160, smem>>>(p, dcol, dval);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
-  std::vector<int> col(p.njb * 128); std::vector<float> val(p.njb * 128);
+  std::vector<int> col(p.njb * 128); std::vector<float> val(p.njb * 128 + 2);
   cudaMemcpy(col.data(), dcol, col.size() * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(val.data(), dval, val.size() * 4, cudaMemcpyDeviceToHost);
   printf("# a_mn=%d b_mn=%d N=%d lbo_a=%u sbo_a=%u lbo_b=%u sbo_b=%u a_tmem=%d\n", p.a_mn, p.b_mn, p.n, p.lbo_a, p.sbo_a, p.lbo_b, p.sbo_b, p.a_tmem);
+  if (p.reps > 0) printf("THROUGHPUT reps=%d: issue %.1f cycles/MMA, issue+complete %.1f cycles/MMA\n", p.reps, val[p.njb * 128], val[p.njb * 128 + 1]);
   for (int jb = 0; jb < p.njb; ++jb) {
     // B float index jb -> column n ; A index (value-1) for m = 0,1,2,3,4,8,127
     if (col[jb * 128] == -1 && argc > 11) continue;
