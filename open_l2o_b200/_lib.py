@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libl2o_b200.so")
+LIB_PATH = os.environ.get("L2O_LIB") or os.path.join(CSRC, "libl2o_b200.so")  # L2O_LIB: A/B-test an alternative build
 INCLUDE = os.path.join(_ROOT, "include")
 
 L2O_OK, L2O_E_INVALID, L2O_E_UNSUPPORTED, L2O_E_CUDA, L2O_E_NOMEM = 0, -1, -2, -3, -4

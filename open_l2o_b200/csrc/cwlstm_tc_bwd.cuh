@@ -17,7 +17,8 @@ namespace tcb {
 using namespace tc;
 
 constexpr int kEpi = 256;
-constexpr int kThreadsB = kEpi + 32;
+constexpr int kThreadsB = kEpi + 128;
+constexpr int kEpiRegs = 224, kIssuerRegs = 40;
 // TMEM column map
 constexpr int cD1 = 0;                   // Z1 accumulators (kept until the layer-1 backward re-reads them)
 constexpr int cD2 = 80;                  // Z2 accumulators, then dX2 / dX1 results (aliased)
@@ -438,9 +439,13 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
   const uint32_t tmem_base = S.tmem_slot;
 
   if (warp < kEpi / 32) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     if (warp < 4) epilogue<C, 0>(a, rt, S, tmem_base, warp, lane);
     else epilogue<C, 1>(a, rt, S, tmem_base, warp, lane);
+  } else if (warp > kEpi / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kIssuerRegs));
   } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kIssuerRegs));
     mbar_wait(&S.wbar, 0);
     {  // warp-uniform issuer (see cwlstm_tc.cuh): elect.sync predicates the MMAs / commits to one lane
       const uint32_t img_s = smem_u32(S.img);
