@@ -331,15 +331,8 @@ class _Program(object):
                 in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
                 h.unroll_bwd(r.net.theta, r.n, T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec)
             if self.opt.distributed:
-                import torch.distributed as dist
-                packed = torch.cat([self.dtheta[k] for k in self.nets] + [fx])
-                dist.all_reduce(packed)
-                off = 0
-                for k in self.nets:
-                    n = self.dtheta[k].numel()
-                    self.dtheta[k].copy_(packed[off:off + n])
-                    off += n
-                fx = packed[off:]
+                from .dist import allreduce_meta_grad
+                fx = allreduce_meta_grad(self.dtheta, fx)
         elif self.opt.distributed:
             import torch.distributed as dist
             fx = fx.clone()
