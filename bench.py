@@ -35,7 +35,7 @@ METRIC = "coordinate-updates/sec (N_params x unroll_steps)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rastrigin", choices=["rastrigin", "lasso", "mlp", "rnnprop_mlp", "quadratic"])
@@ -87,37 +87,47 @@ def make_problem(name, coords, rank):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle-reason sampler for the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clock / throttle-reason sampler (B200_PROFILING.md): one streaming `nvidia-smi -lms` process; only
+    samples whose arrival time falls inside [t_begin, t_end] of the timed region are summarised."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.proc = index, [], None
+        self.t_begin, self.t_end = None, None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.samples.append((time.perf_counter(), parts))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.2)
 
     def summary(self):
-        if not self.samples:
+        inside = [p for (ts, p) in self.samples if self.t_begin is not None and self.t_begin <= ts <= self.t_end]
+        use = inside if inside else [p for (_, p) in self.samples]
+        if not use:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(float(s[0])) for s in self.samples)
+        sm = sorted(int(float(s[0])) for s in use)
         reasons = set()
-        for s in self.samples:
+        for s in use:
             for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(use[0][1])), "reasons": sorted(reasons),
+                "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 def pick_cpu_threads():
@@ -217,11 +227,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") -----------------------------------------------------
-    for _ in range(args.warmup):
-        sess.run(fetch)
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(args.warmup):
+        sess.run(fetch)
     barrier()
+    sampler.t_begin = time.perf_counter()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -229,9 +240,10 @@ def main():
         cost = sess.run(fetch)[0]
     e1.record()
     barrier()
+    sampler.t_end = time.perf_counter()
     launches = eng.launch_count() - l0
     t_dev = e0.elapsed_time(e1) / 1e3
-    sampler.stop_flag = True
+    sampler.stop()
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
