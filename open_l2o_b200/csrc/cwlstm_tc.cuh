@@ -260,7 +260,8 @@ struct Smem {
 };
 
 template <class C>
-__global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args a, NetRt rt, const float* __restrict__ img) {
+__global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args a, NetRt rt, const float* __restrict__ img,
+                                                                  float* __restrict__ state_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
             store_vec<kH>(ck + i * kH, hrow);
             store_vec<kH>(ck + (n + i) * kH, c1);
           }
-          if (t == T - 1) store_vec<kH>(a.state + i * kH, hrow);  // final hidden state of layer 1
+          if (t == T - 1) store_vec<kH>(state_out + i * kH, hrow);  // final hidden state of layer 1
         }
         // ---- layer 2 epilogue + output linear + parameter add ---------------------------------
         mbar_wait(&S.d_ready[tile], pd);
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
             const float r = a.labels[(int64_t)t * n + i] - d;
             imit += 0.5 * (double)r * (double)r;
           }
-          if (t == T - 1) store_vec<kH>(a.state + 2 * n * kH + i * kH, hrow);  // final hidden state of layer 2
+          if (t == T - 1) store_vec<kH>(state_out + 2 * n * kH + i * kH, hrow);  // final hidden state of layer 2
         }
       }
       // ---- tile epilogue: final cell state / x / f(x_T), g_T ------------------------------------
@@ -429,8 +430,8 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
             if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gT;
           }
           if (T > 0) {
-            store_vec<kH>(a.state + (n + i) * kH, c1);
-            store_vec<kH>(a.state + 2 * n * kH + (n + i) * kH, c2);
+            store_vec<kH>(state_out + (n + i) * kH, c1);
+            store_vec<kH>(state_out + 2 * n * kH + (n + i) * kH, c2);
           }
           if (a.x) a.x[i] = x;
         }
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
 
 // ------------------------------------------------------------------ host side (called from l2o_capi.cu)
 template <class C>
-int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms) {
+int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms, float* state_out = nullptr) {
   tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 0);
   auto k = tc::unroll_fwd_kernel<C>;
   const size_t smem = sizeof(tc::Smem) + (size_t)(a.T + 1) * sizeof(double) + 128;
@@ -514,7 +515,7 @@ int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStr
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
   const int64_t npairs = (a.n + tc::kEpiThreads - 1) / tc::kEpiThreads;
   const int grid = (int)(npairs < sms ? npairs : sms);
-  k<<<grid, tc::kThreads, smem, st>>>(a, rt, img);
+  k<<<grid, tc::kThreads, smem, st>>>(a, rt, img, state_out ? state_out : a.state);
   return cudaGetLastError() == cudaSuccess ? L2O_OK : L2O_E_CUDA;
 }
 

@@ -117,7 +117,12 @@ int l2o_step(l2o_handle h, const l2o_step_args* a, void* stream) {
   if ((a->m == nullptr) != (a->v == nullptr)) return L2O_E_INVALID;
   if (a->m && h->desc.n_in != 2) return L2O_E_INVALID;
   if (a->n == 0) return L2O_OK;
-  return l2o::ffma_step(h, *a, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_can = l2o::tc_step_ok(h, *a);
+  if (h->engine == L2O_ENGINE_TC) return tc_can ? l2o::tc_step(h, *a, st) : L2O_E_UNSUPPORTED;
+  // AUTO: the tensor-core path pays a fixed ~10 us (weight image + TMEM setup) per launch; use it for real sizes
+  if (h->engine == L2O_ENGINE_AUTO && tc_can && l2o::tc_auto_default() && a->n >= 16384) return l2o::tc_step(h, *a, st);
+  return l2o::ffma_step(h, *a, st);
 }
 
 int l2o_unroll_fwd(l2o_handle h, const l2o_unroll_args* a, void* stream) {

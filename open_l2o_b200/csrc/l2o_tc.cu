@@ -40,6 +40,35 @@ int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {
   return rc;
 }
 
+bool tc_step_ok(const l2o_net* h, const l2o_step_args& a) {
+  return tc_supported(h->cfg) && a.m == nullptr && a.in1 == nullptr && a.feat_out == nullptr;
+}
+
+// One time step with the state in HBM (external-gradient regime) = the forward unroll with T = 1 and an
+// out-of-place final-state write.
+int tc_step(l2o_net* h, const l2o_step_args& s, cudaStream_t st) {
+  if (!tc_step_ok(h, s)) return L2O_E_UNSUPPORTED;
+  int rc = ensure_image(h);
+  if (rc) return rc;
+  const int sms = device_sms();
+  if (sms <= 0) return L2O_E_CUDA;
+  l2o_unroll_args a{};
+  a.n = s.n;
+  a.T = 1;
+  a.theta = s.theta;
+  a.in_seq = s.in0;
+  a.opt_kind = L2O_OPT_NONE;
+  a.x = s.x;
+  a.state = const_cast<float*>(s.state_in);
+  a.delta_seq = s.delta;
+  rc = L2O_E_UNSUPPORTED;
+  if (h->cfg == 0) rc = tc_launch_fwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out);
+  if (h->cfg == 1) rc = tc_launch_fwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out);
+  if (rc == L2O_OK) count_launch(2);
+  if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_step launch");
+  return rc;
+}
+
 int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st) {
   if (!tc_supported(h->cfg) || !tc_fwd_ok(a)) return L2O_E_UNSUPPORTED;
   {

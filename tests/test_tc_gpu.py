@@ -114,3 +114,34 @@ def test_tc_bwd_matches_ffma_bwd(name):
         torch.cuda.synchronize()
         outs[eng] = d
     assert rel_err(outs[ENGINE_TC], outs[ENGINE_FFMA]) <= REL_TOL
+
+
+@pytest.mark.parametrize("name", ["dm_identity", "dm_logsign"])
+def test_tc_step_operator(name):
+    """l2o_step on the tcgen05 engine (state in HBM, out-of-place) vs the oracle; chained over 3 steps."""
+    from open_l2o_b200.engine import ENGINE_TC
+    from tests.helpers import random_state, state_to_arena, wild_gradients
+    spec = SPECS[name]
+    n = 20000
+    gen = torch.Generator().manual_seed(31)
+    theta = _theta(spec)
+    st = random_state(spec, n, gen)
+    x_ref = torch.randn(n, generator=gen)
+    h = make_handle(spec)
+    h.set_engine(ENGINE_TC)
+    th = theta.to(DEV)
+    a_in = state_to_arena(st, n).to(DEV)
+    x = x_ref.to(DEV).clone()
+    for it in range(3):
+        g = wild_gradients(n, gen) if spec.preprocess_name == "LogAndSign" else torch.randn(n, generator=gen)
+        d_ref, st = orc.net_apply(spec, theta, g.unsqueeze(-1), st)
+        x_ref = x_ref + d_ref
+        a_out = torch.zeros_like(a_in)
+        delta = torch.empty(n, device=DEV)
+        h.step(th, g.to(DEV), a_in, a_out, x=x, delta=delta)
+        torch.cuda.synchronize()
+        assert rel_err(delta, d_ref) <= REL_TOL
+        assert rel_err(x, x_ref) <= REL_TOL
+        for (hg, cg), (hr, cr) in zip(arena_to_state(a_out.cpu(), spec.layers, n), st):
+            assert rel_err(hg, hr) <= REL_TOL and rel_err(cg, cr) <= REL_TOL
+        a_in = a_out
