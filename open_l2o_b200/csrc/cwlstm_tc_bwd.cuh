@@ -307,26 +307,35 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 #pragma unroll
         for (int u = 0; u < 4; ++u) dh2c[4 * g4 + u] = v[u];
       }
-      mbar_wait(&S.w_done, 0);  // dW2 MMAs done: staging may be overwritten
-      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       {
-        float h1p[NU];
+        // compute dz1 and feed the dX1 A operand (TMEM) first; the shared staging is touched only after the dW2 MMAs
+        // have drained, so their ~2K cycles overlap with this phase's arithmetic instead of stalling it
+        float h1p[NU], dz1[4 * NU];
 #pragma unroll
         for (int k = 0; k < NU; ++k) h1p[k] = 0.f;
         if (act) load_vec<NU>(ck + i * kH + U0, h1p);  // re-read (cache hit): cheaper than 12 live registers
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
-          float z[16], g[16];
+          float z[16];
           tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
-          gates4(z, g);
+          gates4(z, dz1 + 16 * g4);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = 4 * g4 + u;
-            const float cn = fmaf(g[4 * u + 2], c1p[k], g[4 * u + 0] * g[4 * u + 1]);
+            float* g = dz1 + 16 * g4 + 4 * u;
+            const float cn = fmaf(g[2], c1p[k], g[0] * g[1]);
             const float tcn = tanh_fast(cn);
-            unit_bwd(g + 4 * u, c1p[k], tcn, dh1[k], dc1c[k]);
-            put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.y_hi, S.y_lo, dz_sidx(c, U0 + k), true, true);
+            unit_bwd(g, c1p[k], tcn, dh1[k], dc1c[k]);
+            put4(tAZh, tAZl, 4 * (U0 + k), g, nullptr, nullptr, 0, true, false);
           }
+        }
+        mbar_wait(&S.w_done, 0);  // dW2 MMAs done: staging may be overwritten
+        if (prof) { L2O_PROF(HALF, pi); ++pi; }
+#pragma unroll
+        for (int g4 = 0; g4 < NU / 4; ++g4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            put4(0, 0, 0, dz1 + 16 * g4 + 4 * u, S.y_hi, S.y_lo, dz_sidx(c, U0 + 4 * g4 + u), false, true);
           put4(0, 0, 0, h1p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
         }
         if (HALF == 1) put4(0, 0, 0, u4, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
