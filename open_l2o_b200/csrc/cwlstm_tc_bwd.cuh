@@ -52,7 +52,7 @@ struct SmemB {
   float y_lo[kYFloats];
   float img[kImgAllFloats];    // B1h|B1l|B2h|B2l (forward, K-major) | T1h|T1l|T2h|T2l (transposed, K-major)
   float wo[kH + 4];
-  uint64_t wbar, a_ready, d_ready, w_done;
+  uint64_t wbar, a_ready, d_ready, w_done, z_ready, f_ready;
   uint32_t tmem_slot, pad;
 };
 static_assert(sizeof(SmemB) + 1024 <= 227 * 1024, "shared memory budget");
@@ -139,6 +139,47 @@ __device__ __forceinline__ void unit_bwd(float* g, float cprev, float tcn, float
   dc = dcv * f;
 }
 
+// Feature/checkpoint phase of one step: loads the checkpointed rows, writes A_F = [u | 1 | h1p | h2p] to TMEM and
+// returns the values later phases need.  It depends only on the checkpoints, so the step loop runs it one step AHEAD
+// (right after the previous step's layer-1 backward) and its Z1 MMAs overlap the previous step's dW1 batch.
+template <class C, int HALF, int NU, int U0>
+__device__ __forceinline__ void feature_phase(const l2o_bwd_args& a, const NetRt& rt, bool act, int64_t i, int64_t n,
+                                              int64_t slot, int t, uint32_t tAFh, uint32_t tAFl, float* u4, float* h2p,
+                                              float* c1p, float* c2p) {
+  const float* ck = a.ckpt + (int64_t)t * slot;
+  {
+    const float raw0 = act ? a.in_seq[(int64_t)t * n + i] : 0.f;
+    float uu[C::F];
+    preprocess<C>(nullptr, rt, raw0, 0.f, uu);
+    u4[0] = u4[1] = u4[2] = u4[3] = 0.f;
+#pragma unroll
+    for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
+    u4[C::F] = 1.0f;
+  }
+  float h1p[NU];
+#pragma unroll
+  for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h2p[k] = 0.f; c1p[k] = 0.f; c2p[k] = 0.f; }
+  if (act) {  // all four checkpoint rows at once: one DRAM latency per step
+    load_vec<NU>(ck + i * kH + U0, h1p);
+    load_vec<NU>(ck + 2 * n * kH + i * kH + U0, h2p);
+    load_vec<NU>(ck + (n + i) * kH + U0, c1p);
+    load_vec<NU>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
+    if (t > 0) {  // pull the following step's rows towards L2
+      const float* nk = ck - slot;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + U0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + U0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + U0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
+    }
+  }
+  if (HALF == 1) put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
+#pragma unroll
+  for (int g4 = 0; g4 < NU / 4; ++g4) {
+    put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
+    put4(tAFh, tAFl, kColH2 + U0 + 4 * g4, h2p + 4 * g4, nullptr, nullptr, 0, true, false);
+  }
+}
+
 template <class C, int HALF>
 __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt, SmemB& S, uint32_t tmem_base, int warp,
                                          int lane) {
@@ -152,15 +193,15 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
   const int64_t n = a.n;
   const int64_t slot = n * C::SF;
   const int64_t ntiles = (n + 127) / 128;
-  uint32_t pd = 0;
-  int pi = 0;  // profile event index
+  uint32_t pd = 0, pz = 0;  // parities of d_ready (Z2, dX2, dX1 in turn) and z_ready (Z1)
+  int pi = 0;               // profile event index
   const bool prof = (q == 0 && lane == 0);
   (void)pi; (void)prof;
   // w_done completes exactly twice per step: dW2 (even completion, parity 0) then dW1 (odd, parity 1)
   float acc_wo[NU], acc_bo = 0.f;
 #pragma unroll
   for (int k = 0; k < NU; ++k) acc_wo[k] = 0.f;
-  // zero the persistent dW accumulators (lane = gate row)
+  // zero the persistent dW accumulators (lane = gate row) and the A pad columns
   if (HALF == 0) {
 #pragma unroll
     for (int k = 0; k < (48 + 32) / 4; ++k) tmem_st4(tl + cW2 + 4 * k, 0.f, 0.f, 0.f, 0.f);
@@ -176,68 +217,33 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 #pragma unroll
     for (int k = 0; k < NU; ++k) { dh1c[k] = 0.f; dc1c[k] = 0.f; dh2c[k] = 0.f; dc2c[k] = 0.f; }
     float lam = act ? a.g_rec[(int64_t)T * n + i] : 0.f;
+    // prologue: feature phase of the first (last-in-time) step of this tile
+    float u4[4], h2p[NU], c1p[NU], c2p[NU];
+    feature_phase<C, HALF, NU, U0>(a, rt, act, i, n, slot, T - 1, tAFh, tAFl, u4, h2p, c1p, c2p);
+    tc_wait_st();
+    tc_fence_before();
+    mbar_arrive(&S.f_ready);
 
     for (int t = T - 1; t >= 0; --t) {
       const float* ck = a.ckpt + (int64_t)t * slot;
-      // ---------------- P0: A_F <- [u | 1 | h1p | h2p] ----------------
-      float u4[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        float raw0 = act ? a.in_seq[(int64_t)t * n + i] : 0.f;
-        float uu[C::F];
-        preprocess<C>(nullptr, rt, raw0, 0.f, uu);
-#pragma unroll
-        for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
-        u4[C::F] = 1.0f;
-      }
-      float h2p[NU], c1p[NU], c2p[NU];
-      {
-        float h1p[NU];
-#pragma unroll
-        for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h2p[k] = 0.f; c1p[k] = 0.f; c2p[k] = 0.f; }
-        if (act) {  // all four checkpoint rows at once: one exposed DRAM latency per step
-          load_vec<NU>(ck + i * kH + U0, h1p);
-          load_vec<NU>(ck + 2 * n * kH + i * kH + U0, h2p);
-          load_vec<NU>(ck + (n + i) * kH + U0, c1p);
-          load_vec<NU>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
-          if (t > 0) {  // pull the next step's rows towards L2 while this step computes
-            const float* nk = ck - slot;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + U0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + U0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + U0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
-          }
-        }
-        if (HALF == 1) put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
-#pragma unroll
-        for (int g4 = 0; g4 < NU / 4; ++g4) {
-          put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
-          put4(tAFh, tAFl, kColH2 + U0 + 4 * g4, h2p + 4 * g4, nullptr, nullptr, 0, true, false);
-        }
-      }
-      if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(&S.a_ready);
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
       // ---------------- P1: h1n = LSTM1 forward (only what layer 2 needs) ----------------
       float h1n[NU];
-      mbar_wait(&S.d_ready, pd);
-      pd ^= 1;
+      mbar_wait(&S.z_ready, pz);
+      pz ^= 1;
       tc_fence_after();
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      {
 #pragma unroll
-        for (int g4 = 0; g4 < NU / 4; ++g4) {
-          float z[16], g[16];
-          tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
-          gates4(z, g);
+      for (int g4 = 0; g4 < NU / 4; ++g4) {
+        float z[16], g[16];
+        tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
+        gates4(z, g);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float cn = fmaf(g[4 * u + 2], c1p[4 * g4 + u], g[4 * u + 0] * g[4 * u + 1]);
-            h1n[4 * g4 + u] = tanh_fast(cn) * g[4 * u + 3];
-          }
-          put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1n + 4 * g4, nullptr, nullptr, 0, true, false);
+        for (int u = 0; u < 4; ++u) {
+          const float cn = fmaf(g[4 * u + 2], c1p[4 * g4 + u], g[4 * u + 0] * g[4 * u + 1]);
+          h1n[4 * g4 + u] = tanh_fast(cn) * g[4 * u + 3];
         }
+        put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1n + 4 * g4, nullptr, nullptr, 0, true, false);
       }
       tc_wait_st();
       tc_fence_before();
@@ -248,7 +254,6 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       pd ^= 1;
       tc_fence_after();
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-
       const float dy = rt.scale * lam;  // dDelta_t = sum_{tau>t} g_tau ; linear output (tanh_output handled by FFMA engine)
       if (HALF == 1) acc_bo += dy;
       // staging buffers must be free: the dW1 MMAs of the previous step have completed
@@ -295,7 +300,6 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       pd ^= 1;
       tc_fence_after();
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-
       float dh1[NU];
 #pragma unroll
       for (int g4 = 0; g4 < NU / 4; ++g4) {
@@ -345,12 +349,20 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       tc_fence_before();
       mbar_arrive(&S.a_ready);
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
+      // ---------------- P0 of the NEXT step (t-1), one step ahead: its Z1 MMAs are issued before this step's dW1 ----
+      if (act) lam += a.g_rec[(int64_t)t * n + i];
+      if (t > 0) {
+        feature_phase<C, HALF, NU, U0>(a, rt, act, i, n, slot, t - 1, tAFh, tAFl, u4, h2p, c1p, c2p);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&S.f_ready);
+      }
+      if (prof) { L2O_PROF(HALF, pi); ++pi; }
       // ---------------- P4: carry for step t-1 ----------------
       mbar_wait(&S.d_ready, pd);
       pd ^= 1;
       tc_fence_after();
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-
 #pragma unroll
       for (int g4 = 0; g4 < NU / 4; ++g4) {
         float v[4];
@@ -358,7 +370,6 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 #pragma unroll
         for (int u = 0; u < 4; ++u) dh1c[4 * g4 + u] = v[u];
       }
-      if (act) lam += a.g_rec[(int64_t)t * n + i];
     }
   }
   // ---------------- flush: output-layer gradient from registers ----------------
@@ -431,6 +442,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
       mbar_init(&S.a_ready, kEpi);
       mbar_init(&S.d_ready, 1);
       mbar_init(&S.w_done, 1);
+      mbar_init(&S.z_ready, 1);
+      mbar_init(&S.f_ready, kEpi);
       fence_barrier_init();
     }
     __syncwarp();
@@ -477,25 +490,27 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
       constexpr uint64_t kYStep = (2 * kYSBO) >> 4;       // 8 coordinates = two K atoms
       const uint32_t tD1 = tmem_base + cD1, tD2 = tmem_base + cD2, tAFh = tmem_base + cAFh, tAFl = tmem_base + cAFl;
       const uint32_t tAZh = tmem_base + cAZh, tAZl = tmem_base + cAZl, tW2 = tmem_base + cW2, tW1 = tmem_base + cW1;
-      uint32_t pa = 0;
+      uint32_t pa = 0, pf = 0;
       int pi = 0;
       (void)pi;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int t = T - 1; t >= 0; --t) {
-          // Z1
-          mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
-          L2O_PROF(2, pi); ++pi;
-          if (elect_one()) {
+      // Z1 of one step: waits for the feature phase (f_ready), signals z_ready
+      auto issue_z1 = [&]() {
+        mbar_wait(&S.f_ready, pf); pf ^= 1; tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-            for (int kc = 0; kc < kK1 / 8; ++kc) {
-              mma_tf32_ts(tD1, tAFl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
-              mma_tf32_ts(tD1, tAFh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
-              mma_tf32_ts(tD1, tAFh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
-            }
-            tc_commit(&S.d_ready);
+          for (int kc = 0; kc < kK1 / 8; ++kc) {
+            mma_tf32_ts(tD1, tAFl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+            mma_tf32_ts(tD1, tAFh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
+            mma_tf32_ts(tD1, tAFh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
           }
-          __syncwarp();
-          L2O_PROF(2, pi); ++pi;
+          tc_commit(&S.z_ready);
+        }
+        __syncwarp();
+      };
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        issue_z1();  // tile prologue
+        L2O_PROF(2, pi); ++pi;
+        for (int t = T - 1; t >= 0; --t) {
           // Z2
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
           L2O_PROF(2, pi); ++pi;
@@ -535,7 +550,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
           }
           __syncwarp();
           L2O_PROF(2, pi); ++pi;
-          // dX1 = dZ1 . W1^T   and   dW1^T += dZ1^T . X1
+          // dX1 = dZ1 . W1^T
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
           L2O_PROF(2, pi); ++pi;
           if (elect_one()) {
@@ -549,6 +564,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
           }
           __syncwarp();
           L2O_PROF(2, pi); ++pi;
+          // Z1 of the NEXT step goes ahead of this step's (long, off-critical-path) dW1 batch
+          if (t > 0) issue_z1();
+          L2O_PROF(2, pi); ++pi;
+          // dW1^T += dZ1^T . X1
           if (elect_one()) {
 #pragma unroll
             for (int kb = 0; kb < 16; ++kb) {
