@@ -149,5 +149,14 @@ def log_and_sign(g: torch.Tensor, k: float) -> torch.Tensor:
     return out
 
 
+_graph_replayed = 0  # kernels of this library launched through CUDA-graph replays (not visible to the C-side counter)
+
+
+def note_graph_replay(kernels_in_graph: int):
+    global _graph_replayed
+    _graph_replayed += int(kernels_in_graph)
+
+
 def launch_count() -> int:
-    return int(_lib.lib().l2o_launch_count())
+    """Kernels of this library launched so far: direct C-ABI launches + kernels replayed inside captured graphs."""
+    return int(_lib.lib().l2o_launch_count()) + _graph_replayed

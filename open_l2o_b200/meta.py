@@ -187,6 +187,7 @@ class _Program(object):
                        for k, net in self.nets.items()}
         self.step_placeholder = Placeholder("step")
         self.unroll_idx = 0
+        self._graphs, self._eager_calls, self._graph_failed, self._graph_kernels = {}, {}, False, {}
         self._alloc_workspaces()
         self.reset()
 
@@ -311,6 +312,56 @@ class _Program(object):
         self._Xw = Xw
         return torch.stack([f.reshape(()).double() for f in fxs])
 
+    # ---- CUDA-graph path of the external-gradient regime ------------------------------------------------
+    def _graph_body(self, train, step0):
+        """Everything of one unroll that is launch-bound and shape-static: T x (autograd + step kernel) [+ BPTT]."""
+        fx = self._forward_external(train, step0)
+        if train:
+            for d in self.dtheta.values():
+                d.zero_()
+            for r in self.runs:
+                h = r.net.handle
+                in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
+                h.unroll_bwd(r.net.theta, r.n, self.T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec)
+        return fx
+
+    def _graph_eligible(self):
+        # RNNProp's bias-correction exponent p = step + t is a host scalar that changes every unroll -> stays eager
+        return (os.environ.get("L2O_CUDA_GRAPH", "1") != "0" and self.fused is None
+                and all(r.net.handle.n_in == 1 for r in self.runs))
+
+    def _run_external(self, train, step0):
+        """Eager on the first two calls (warm-up: lazy allocations, autograd caches), then capture once per mode and
+        replay: the per-step launches (~15 tiny kernels) collapse into one graph launch."""
+        key = bool(train)
+        if not self._graph_eligible() or self._graph_failed:
+            return self._graph_body(train, step0)
+        self._eager_calls[key] = self._eager_calls.get(key, 0) + 1
+        if self._eager_calls[key] <= 2:
+            return self._graph_body(train, step0)
+        if key not in self._graphs:
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = _engine.launch_count()
+                with torch.cuda.graph(g):
+                    fx = self._graph_body(train, step0)
+                self._graph_kernels[key] = _engine.launch_count() - n0   # library kernels recorded in this graph
+                self._graphs[key] = (g, fx, self._Xw, [r.state_final for r in self.runs], [r.x_work for r in self.runs])
+            except Exception as e:  # capture not possible for this optimizee: keep running the same kernels eagerly
+                import warnings
+                warnings.warn("CUDA-graph capture of the unroll failed (%r); staying eager" % (e,))
+                self._graph_failed = True
+                torch.cuda.synchronize()
+                return self._graph_body(train, step0)
+        g, fx, xw, finals, xworks = self._graphs[key]
+        g.replay()
+        _engine.note_graph_replay(self._graph_kernels[key])
+        self._Xw = xw
+        for r, f, xk in zip(self.runs, finals, xworks):
+            r.state_final, r.x_work = f, xk
+        return fx
+
     def execute(self, kinds, feed):
         if kinds == {"reset"}:
             self.reset()
@@ -321,15 +372,19 @@ class _Program(object):
         commit = "update" in kinds
         step0 = self._step0(feed)
         T = self.T
-        fx = self._forward_fused(train, step0) if self.fused is not None else self._forward_external(train, step0)
         out = {}
+        if self.fused is not None:
+            fx = self._forward_fused(train, step0)
+            if train:
+                for d in self.dtheta.values():
+                    d.zero_()
+                for r in self.runs:
+                    h = r.net.handle
+                    in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
+                    h.unroll_bwd(r.net.theta, r.n, T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec)
+        else:
+            fx = self._run_external(train, step0)
         if train:
-            for d in self.dtheta.values():
-                d.zero_()
-            for r in self.runs:
-                h = r.net.handle
-                in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
-                h.unroll_bwd(r.net.theta, r.n, T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec)
             if self.opt.distributed:
                 from .dist import allreduce_meta_grad
                 fx = allreduce_meta_grad(self.dtheta, fx)
