@@ -21,8 +21,10 @@ namespace l2o {
 namespace tc {
 
 constexpr int kTiles = 2;                    // coordinate tiles per CTA
-constexpr int kEpiThreads = 128 * kTiles;
-constexpr int kThreads = kEpiThreads + 32;   // + MMA / alloc warp
+constexpr int kTileCoords = 128 * kTiles;    // coordinates per CTA pass
+constexpr int kEpiThreads = 256 * kTiles;    // a thread PAIR per coordinate (hidden units 0..11 | 12..19)
+constexpr int kThreads = kEpiThreads + 128;  // + the warpgroup that holds the MMA / alloc warp (3 idle warps)
+constexpr int kFwdEpiRegs = 112, kFwdIssuerRegs = 32;  // setmaxnreg targets (pool: 640 threads x 96)
 constexpr int kH = 20;
 constexpr int kN = 4 * kH;                   // 80 gate columns
 constexpr int kXC = 4;                       // feature chunk: cols [0, kXC): features, then the constant 1
@@ -248,9 +250,20 @@ __device__ __forceinline__ void st_split4(uint32_t a_hi, uint32_t a_lo, int col,
   tmem_st4(a_lo + col, l0, l1, l2, l3);
 }
 
+__device__ __forceinline__ void lstm_unit_fwd(const float* z, float& c, float& h) {
+  const float i = sigmoid_fast(z[0]);
+  const float j = tanh_fast(z[1]);
+  const float f = sigmoid_fast(z[2] + 1.0f);
+  const float o = sigmoid_fast(z[3]);
+  const float cn = fmaf(f, c, i * j);
+  c = cn;
+  h = tanh_fast(cn) * o;
+}
+
 struct Smem {
   float img[kImgFloats];          // must stay first (16B-aligned TMA destination, descriptor base)
   float wo[kH + 4];               // linear/w, linear/b
+  float ypart[kTiles][2][128];    // output-layer partial sums exchanged inside a thread pair
   uint64_t wbar;
   uint64_t a_ready[kTiles];
   uint64_t d_ready[kTiles];
@@ -258,6 +271,177 @@ struct Smem {
   uint32_t pad;
   double fx[1];                   // [T+1], dynamic tail
 };
+
+// Epilogue of one thread: coordinate `row` of tile `tile`, hidden units [U0, U0+NU) of both layers.
+template <class C, int HALF>
+__device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const NetRt& rt, Smem& S, uint32_t tmem_base,
+                                             float* __restrict__ state_out, int warp, int lane) {
+  constexpr int U0 = HALF == 0 ? 0 : 12;
+  constexpr int NU = HALF == 0 ? 12 : 8;
+  const int tile = warp >> 3;          // warps 0-7: tile 0, 8-15: tile 1
+  const int q = warp & 3;              // TMEM lane quarter
+  const int row = q * 32 + lane;       // coordinate within the tile
+  const int T = a.T;
+  const int64_t n = a.n;
+  const int64_t npairs = (n + kTileCoords - 1) / kTileCoords;
+  const bool in_kernel_opt = a.opt_kind != L2O_OPT_NONE;
+  const bool want_fx = in_kernel_opt && a.fx != nullptr;
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  const uint32_t t_d = tmem_base + lane_off + tile * kTileCols;
+  const uint32_t t_ah = t_d + kN;
+  const uint32_t t_al = t_ah + kACols;
+  uint32_t pd = 0;  // d_ready parity
+  const int64_t slot = n * C::SF;
+  double imit = 0.0;
+  if (HALF == 1) {  // zero the 4 pad columns of A once (they meet zero weight rows, but must be finite)
+    tmem_st4(t_ah + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
+    tmem_st4(t_al + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const int64_t i = pair * kTileCoords + tile * 128 + row;
+    const bool act = i < n;
+    float c1[NU], c2[NU];
+    float x = 0.f, oa = 0.f, ob = 0.f;
+    {
+      float h1[NU], h2[NU];
+#pragma unroll
+      for (int k = 0; k < NU; ++k) { h1[k] = 0.f; h2[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
+      if (act) {
+        load_vec<NU>(a.state + i * kH + U0, h1);
+        load_vec<NU>(a.state + (n + i) * kH + U0, c1);
+        load_vec<NU>(a.state + 2 * n * kH + i * kH + U0, h2);
+        load_vec<NU>(a.state + 2 * n * kH + (n + i) * kH + U0, c2);
+        if (a.ckpt) {
+          store_vec<NU>(a.ckpt + i * kH + U0, h1);
+          store_vec<NU>(a.ckpt + (n + i) * kH + U0, c1);
+          store_vec<NU>(a.ckpt + 2 * n * kH + i * kH + U0, h2);
+          store_vec<NU>(a.ckpt + 2 * n * kH + (n + i) * kH + U0, c2);
+        }
+        if (a.x) x = a.x[i];
+        if (in_kernel_opt) { oa = a.opt_a[i]; ob = a.opt_b[i]; }
+      }
+#pragma unroll
+      for (int g4 = 0; g4 < NU / 4; ++g4) {
+        st_split4(t_ah, t_al, kColH1 + U0 + 4 * g4, h1 + 4 * g4);
+        st_split4(t_ah, t_al, kColH2 + U0 + 4 * g4, h2 + 4 * g4);
+      }
+    }
+    for (int t = 0; t < T; ++t) {
+      // ---- gradient + preprocessing -> feature chunk of A (half 1 owns the per-coordinate scalars) ----------
+      float fval = 0.f;
+      if (HALF == 1) {
+        float raw0 = 0.f;
+        if (act) {
+          if (in_kernel_opt) {
+            optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, raw0);
+            if (a.g_rec) a.g_rec[(int64_t)t * n + i] = raw0;
+          } else {
+            raw0 = a.in_seq[(int64_t)t * n + i];
+          }
+        }
+        float u[4] = {0.f, 0.f, 0.f, 0.f};
+        float dummy[C::F];
+        preprocess<C>(nullptr, rt, raw0, 0.f, dummy);
+#pragma unroll
+        for (int k = 0; k < C::F; ++k) u[k] = dummy[k];
+        u[C::F] = 1.0f;  // bias column
+        st_split4(t_ah, t_al, 0, u);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&S.a_ready[tile]);
+      if (HALF == 1 && want_fx) {
+        const double ws = warp_sum_d((double)fval);
+        if (lane == 0) atomicAdd(&S.fx[t], ws);
+      }
+      // ---- layer 1 epilogue ---------------------------------------------------------------
+      mbar_wait(&S.d_ready[tile], pd);
+      pd ^= 1;
+      tc_fence_after();
+      float hrow[NU];
+#pragma unroll
+      for (int g4 = 0; g4 < NU / 4; ++g4) {
+        float z[16];
+        tmem_ld16(t_d + 4 * U0 + 16 * g4, z);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) lstm_unit_fwd(z + 4 * u, c1[4 * g4 + u], hrow[4 * g4 + u]);
+        st_split4(t_ah, t_al, kColH1 + U0 + 4 * g4, hrow + 4 * g4);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&S.a_ready[tile]);
+      if (act) {
+        if (a.ckpt) {
+          float* ck = a.ckpt + (int64_t)(t + 1) * slot;
+          store_vec<NU>(ck + i * kH + U0, hrow);
+          store_vec<NU>(ck + (n + i) * kH + U0, c1);
+        }
+        if (t == T - 1) store_vec<NU>(state_out + i * kH + U0, hrow);  // final hidden state of layer 1
+      }
+      // ---- layer 2 epilogue + output linear + parameter add ---------------------------------
+      mbar_wait(&S.d_ready[tile], pd);
+      pd ^= 1;
+      tc_fence_after();
+      float yp = 0.f;
+#pragma unroll
+      for (int g4 = 0; g4 < NU / 4; ++g4) {
+        float z[16];
+        tmem_ld16(t_d + 4 * U0 + 16 * g4, z);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          lstm_unit_fwd(z + 4 * u, c2[4 * g4 + u], hrow[4 * g4 + u]);
+          yp = fmaf(hrow[4 * g4 + u], S.wo[U0 + 4 * g4 + u], yp);
+        }
+        st_split4(t_ah, t_al, kColH2 + U0 + 4 * g4, hrow + 4 * g4);
+      }
+      // exchange the output-layer partial sums inside the thread pair (named barrier: the tile's 256 threads)
+      S.ypart[tile][HALF][row] = yp;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
+      const float y = (S.ypart[tile][0][row] + S.ypart[tile][1][row]) + S.wo[kH];
+      const float d = rt.tanh_output ? tanh_acc(y) * rt.scale : y * rt.scale;
+      x += d;
+      if (act) {
+        if (a.ckpt) {
+          float* ck = a.ckpt + (int64_t)(t + 1) * slot + 2 * n * kH;
+          store_vec<NU>(ck + i * kH + U0, hrow);
+          store_vec<NU>(ck + (n + i) * kH + U0, c2);
+        }
+        if (t == T - 1) store_vec<NU>(state_out + 2 * n * kH + i * kH + U0, hrow);  // final hidden state of layer 2
+        if (HALF == 1) {
+          if (a.delta_seq) a.delta_seq[(int64_t)t * n + i] = d;
+          if (a.labels) {
+            const float r = a.labels[(int64_t)t * n + i] - d;
+            imit += 0.5 * (double)r * (double)r;
+          }
+        }
+      }
+    }
+    // ---- tile epilogue: final cell state / x / f(x_T), g_T ------------------------------------
+    {
+      float fval = 0.f;
+      if (act) {
+        if (HALF == 1 && in_kernel_opt) {
+          float gT;
+          optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, gT);
+          if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gT;
+        }
+        if (T > 0) {
+          store_vec<NU>(state_out + (n + i) * kH + U0, c1);
+          store_vec<NU>(state_out + 2 * n * kH + (n + i) * kH + U0, c2);
+        }
+        if (HALF == 1 && a.x) a.x[i] = x;
+      }
+      if (HALF == 1 && want_fx) {
+        const double ws = warp_sum_d((double)fval);
+        if (lane == 0) atomicAdd(&S.fx[T], ws);
+      }
+    }
+  }
+  if (HALF == 1 && a.labels && a.imit_loss) {
+    const double ws = warp_sum_d(imit);
+    if (lane == 0) atomicAdd(a.imit_loss, ws / (double)a.n_total);
+  }
+}
 
 template <class C>
 __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args a, NetRt rt, const float* __restrict__ img,
@@ -267,20 +451,20 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = a.T;
   const int64_t n = a.n;
-  const int64_t npairs = (n + kEpiThreads - 1) / kEpiThreads;
-  const bool in_kernel_opt = a.opt_kind != L2O_OPT_NONE;
-  const bool want_fx = in_kernel_opt && a.fx != nullptr;
+  const int64_t npairs = (n + kTileCoords - 1) / kTileCoords;
+  const bool want_fx = a.opt_kind != L2O_OPT_NONE && a.fx != nullptr;
+  constexpr int kIssuerWarp = kEpiThreads / 32;
 
   if (want_fx)
     for (int t = threadIdx.x; t <= T; t += blockDim.x) S.fx[t] = 0.0;
   if (threadIdx.x < kH) S.wo[threadIdx.x] = a.theta[C::O_WO + threadIdx.x];
   if (threadIdx.x == kH) S.wo[kH] = a.theta[C::O_BO];
-  if (warp == kEpiThreads / 32) {
+  if (warp == kIssuerWarp) {
     if (lane == 0) {
       mbar_init(&S.wbar, 1);
 #pragma unroll
       for (int k = 0; k < kTiles; ++k) {
-        mbar_init(&S.a_ready[k], 128);
+        mbar_init(&S.a_ready[k], 256);
         mbar_init(&S.d_ready[k], 1);
       }
       fence_barrier_init();
@@ -298,155 +482,16 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_slot;
 
-  if (warp < kEpiThreads / 32) {
-    // =============================== epilogue warps: thread == coordinate ===============================
-    const int tile = warp >> 2;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t t_d = tmem_base + lane_off + tile * kTileCols;
-    const uint32_t t_ah = t_d + kN;
-    const uint32_t t_al = t_ah + kACols;
-    uint32_t pd = 0;  // d_ready parity
-    const int64_t slot = n * C::SF;
-    double imit = 0.0;
-    // zero the 4 pad columns of A once (they meet zero weight rows, but must be finite)
-    tmem_st4(t_ah + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
-    tmem_st4(t_al + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int64_t i = pair * kEpiThreads + tile * 128 + (warp & 3) * 32 + lane;
-      const bool act = i < n;
-      float c1[kH], c2[kH];
-      float x = 0.f, oa = 0.f, ob = 0.f;
-      {
-        float h1[kH], h2[kH];
-#pragma unroll
-        for (int k = 0; k < kH; ++k) { h1[k] = 0.f; h2[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
-        if (act) {
-          load_vec<kH>(a.state + i * kH, h1);
-          load_vec<kH>(a.state + (n + i) * kH, c1);
-          load_vec<kH>(a.state + 2 * n * kH + i * kH, h2);
-          load_vec<kH>(a.state + 2 * n * kH + (n + i) * kH, c2);
-          if (a.ckpt) {
-            store_vec<kH>(a.ckpt + i * kH, h1);
-            store_vec<kH>(a.ckpt + (n + i) * kH, c1);
-            store_vec<kH>(a.ckpt + 2 * n * kH + i * kH, h2);
-            store_vec<kH>(a.ckpt + 2 * n * kH + (n + i) * kH, c2);
-          }
-          if (a.x) x = a.x[i];
-          if (in_kernel_opt) { oa = a.opt_a[i]; ob = a.opt_b[i]; }
-        }
-#pragma unroll
-        for (int q = 0; q < kH / 4; ++q) {
-          st_split4(t_ah, t_al, kColH1 + 4 * q, h1 + 4 * q);
-          st_split4(t_ah, t_al, kColH2 + 4 * q, h2 + 4 * q);
-        }
-      }
-      for (int t = 0; t < T; ++t) {
-        // ---- gradient + preprocessing -> feature chunk of A -------------------------------------
-        float fval = 0.f, raw0 = 0.f;
-        if (act) {
-          if (in_kernel_opt) {
-            optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, raw0);
-            if (a.g_rec) a.g_rec[(int64_t)t * n + i] = raw0;
-          } else {
-            raw0 = a.in_seq[(int64_t)t * n + i];
-          }
-        }
-        {
-          float u[4] = {0.f, 0.f, 0.f, 0.f};
-          float dummy[C::F];
-          preprocess<C>(nullptr, rt, raw0, 0.f, dummy);
-#pragma unroll
-          for (int k = 0; k < C::F; ++k) u[k] = dummy[k];
-          u[C::F] = 1.0f;  // bias column
-          st_split4(t_ah, t_al, 0, u);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&S.a_ready[tile]);
-        if (want_fx) {
-          const double ws = warp_sum_d((double)fval);
-          if (lane == 0) atomicAdd(&S.fx[t], ws);
-        }
-        // ---- layer 1 epilogue ---------------------------------------------------------------
-        mbar_wait(&S.d_ready[tile], pd);
-        pd ^= 1;
-        tc_fence_after();
-        float hrow[kH];
-#pragma unroll
-        for (int q = 0; q < kH / 4; ++q) {
-          float z[16];
-          tmem_ld16(t_d + 16 * q, z);
-          lstm_units4(z, c1 + 4 * q, hrow + 4 * q);
-          st_split4(t_ah, t_al, kColH1 + 4 * q, hrow + 4 * q);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&S.a_ready[tile]);
-        if (act) {
-          if (a.ckpt) {
-            float* ck = a.ckpt + (int64_t)(t + 1) * slot;
-            store_vec<kH>(ck + i * kH, hrow);
-            store_vec<kH>(ck + (n + i) * kH, c1);
-          }
-          if (t == T - 1) store_vec<kH>(state_out + i * kH, hrow);  // final hidden state of layer 1
-        }
-        // ---- layer 2 epilogue + output linear + parameter add ---------------------------------
-        mbar_wait(&S.d_ready[tile], pd);
-        pd ^= 1;
-        tc_fence_after();
-        float y = S.wo[kH];
-#pragma unroll
-        for (int q = 0; q < kH / 4; ++q) {
-          float z[16];
-          tmem_ld16(t_d + 16 * q, z);
-          lstm_units4(z, c2 + 4 * q, hrow + 4 * q);
-          st_split4(t_ah, t_al, kColH2 + 4 * q, hrow + 4 * q);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) y = fmaf(hrow[4 * q + k], S.wo[4 * q + k], y);
-        }
-        const float d = rt.tanh_output ? tanh_acc(y) * rt.scale : y * rt.scale;
-        x += d;
-        if (act) {
-          if (a.ckpt) {
-            float* ck = a.ckpt + (int64_t)(t + 1) * slot + 2 * n * kH;
-            store_vec<kH>(ck + i * kH, hrow);
-            store_vec<kH>(ck + (n + i) * kH, c2);
-          }
-          if (a.delta_seq) a.delta_seq[(int64_t)t * n + i] = d;
-          if (a.labels) {
-            const float r = a.labels[(int64_t)t * n + i] - d;
-            imit += 0.5 * (double)r * (double)r;
-          }
-          if (t == T - 1) store_vec<kH>(state_out + 2 * n * kH + i * kH, hrow);  // final hidden state of layer 2
-        }
-      }
-      // ---- tile epilogue: final cell state / x / f(x_T), g_T ------------------------------------
-      {
-        float fval = 0.f;
-        if (act) {
-          if (in_kernel_opt) {
-            float gT;
-            optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, gT);
-            if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gT;
-          }
-          if (T > 0) {
-            store_vec<kH>(state_out + (n + i) * kH, c1);
-            store_vec<kH>(state_out + 2 * n * kH + (n + i) * kH, c2);
-          }
-          if (a.x) a.x[i] = x;
-        }
-        if (want_fx) {
-          const double ws = warp_sum_d((double)fval);
-          if (lane == 0) atomicAdd(&S.fx[T], ws);
-        }
-      }
-    }
-    if (a.labels && a.imit_loss) {
-      const double ws = warp_sum_d(imit);
-      if (lane == 0) atomicAdd(a.imit_loss, ws / (double)a.n_total);
-    }
+  if (warp < kIssuerWarp) {
+    // =============================== epilogue warps: a thread pair per coordinate ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFwdEpiRegs));
+    if (((warp >> 2) & 1) == 0) fwd_epilogue<C, 0>(a, rt, S, tmem_base, state_out, warp, lane);
+    else fwd_epilogue<C, 1>(a, rt, S, tmem_base, state_out, warp, lane);
+  } else if (warp > kIssuerWarp) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFwdIssuerRegs));  // idle warps of the issuer warpgroup
   } else {
     // =============================== MMA issuer warp ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFwdIssuerRegs));
     // The whole warp runs this loop (warp-uniform => descriptors live in uniform registers and the UTCHMMA issue
     // rate matches the tensor pipe); elect.sync picks the one lane whose tcgen05.mma / commit take effect.
     mbar_wait(&S.wbar, 0);  // weights landed (TMA complete_tx)
@@ -500,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
   tc_fence_after();
   if (want_fx)
     for (int t = threadIdx.x; t <= T; t += blockDim.x) atomicAdd(&a.fx[t], S.fx[t]);
-  if (warp == kEpiThreads / 32) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kIssuerWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace tc
@@ -513,7 +558,7 @@ int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStr
   const size_t smem = sizeof(tc::Smem) + (size_t)(a.T + 1) * sizeof(double) + 128;
   if (smem > 220 * 1024) return L2O_E_INVALID;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
-  const int64_t npairs = (a.n + tc::kEpiThreads - 1) / tc::kEpiThreads;
+  const int64_t npairs = (a.n + tc::kTileCoords - 1) / tc::kTileCoords;
   const int grid = (int)(npairs < sms ? npairs : sms);
   k<<<grid, tc::kThreads, smem, st>>>(a, rt, img, state_out ? state_out : a.state);
   return cudaGetLastError() == cudaSuccess ? L2O_OK : L2O_E_CUDA;

@@ -93,7 +93,6 @@ __device__ __forceinline__ float4 split4_hi(const float* v, float4& lo) {
   split_tf32(v[1], h1, lo.y);
   split_tf32(v[2], h2, lo.z);
   split_tf32(v[3], h3, lo.w);
-  lo.x = to_tf32(lo.x); lo.y = to_tf32(lo.y); lo.z = to_tf32(lo.z); lo.w = to_tf32(lo.w);
   return make_float4(h0, h1, h2, h3);
 }
 // 4 values -> TMEM A columns (hi/lo) and, optionally, the MN-major smem staging (hi/lo) at float index `sidx`
@@ -242,6 +241,8 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
         for (int u = 0; u < 4; ++u) {
           const float cn = fmaf(g[4 * u + 2], c1p[4 * g4 + u], g[4 * u + 0] * g[4 * u + 1]);
           h1n[4 * g4 + u] = tanh_fast(cn) * g[4 * u + 3];
+          // park the ACTIVATED gates in the Z1 accumulator columns: the layer-1 backward phase reads them back
+          tmem_st4(tD1 + 4 * U0 + 16 * g4 + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
         }
         put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1n + 4 * g4, nullptr, nullptr, 0, true, false);
       }
@@ -320,9 +321,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
         if (act) load_vec<NU>(ck + i * kH + U0, h1p);  // re-read (cache hit): cheaper than 12 live registers
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
-          float z[16];
-          tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
-          gates4(z, dz1 + 16 * g4);
+          tmem_ld16(tD1 + 4 * U0 + 16 * g4, dz1 + 16 * g4);  // activated gates parked by P1
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = 4 * g4 + u;
