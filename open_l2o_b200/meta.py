@@ -186,6 +186,11 @@ class _Program(object):
         self.dtheta = {k: torch.zeros(net.theta.numel(), dtype=torch.float64, device=self.device)
                        for k, net in self.nets.items()}
         self.step_placeholder = Placeholder("step")
+        # per-variable scale placeholders (random-scaling trick, DM/meta_dm_train.py:336-338,384-385): fx = f(x * scale)
+        self.scale_placeholders = [Placeholder(v["name"] + "_scale") for v in self.variables]
+        self.scale_flat = torch.ones(self.N, device=self.device)
+        self.scale_active = False
+        self.mt_tasks = []
         self.unroll_idx = 0
         self._graphs, self._eager_calls, self._graph_failed, self._graph_kernels = {}, {}, False, {}
         self._alloc_workspaces()
@@ -235,8 +240,36 @@ class _Program(object):
                 return Xflat[o:o + n].view(shape)
             return self.const_vals[name]
 
+        if self.scale_active:
+            Xflat = Xflat * self.scale_flat
         with variable_getter(getter):
             return self.make_loss()
+
+    def _apply_scale_feed(self, feed):
+        fed = [p for p in self.scale_placeholders if p in feed]
+        if not fed:
+            if self.scale_active:
+                self.scale_flat.fill_(1.0)
+                self.scale_active = False
+            return
+        self.scale_flat.fill_(1.0)
+        for j, p in enumerate(self.scale_placeholders):
+            if p in feed:
+                n = int(np.prod(self.variables[j]["shape"])) if self.variables[j]["shape"] else 1
+                o = self.var_off[j]
+                self.scale_flat[o:o + n].copy_(torch.as_tensor(np.asarray(feed[p], dtype=np.float32)).reshape(-1))
+        self.scale_active = True
+
+    def assign_x(self, values):
+        """assign_func of DM/train_dm.py:101-113: overwrite the optimizee variables (list in creation order)."""
+        for j, val in enumerate(values):
+            n = int(np.prod(self.variables[j]["shape"])) if self.variables[j]["shape"] else 1
+            o = self.var_off[j]
+            self.X[o:o + n].copy_(torch.as_tensor(np.asarray(val, dtype=np.float32)).reshape(-1))
+
+    def x_values(self):
+        return [self.X[self.var_off[j]:self.var_off[j] + (int(np.prod(v["shape"])) if v["shape"] else 1)]
+                .reshape(v["shape"]).cpu().numpy() for j, v in enumerate(self.variables)]
 
     def _value_and_grad(self, Xflat):
         Xl = Xflat.detach().requires_grad_(True)
@@ -327,7 +360,7 @@ class _Program(object):
 
     def _graph_eligible(self):
         # RNNProp's bias-correction exponent p = step + t is a host scalar that changes every unroll -> stays eager
-        return (os.environ.get("L2O_CUDA_GRAPH", "1") != "0" and self.fused is None
+        return (os.environ.get("L2O_CUDA_GRAPH", "1") != "0" and self.fused is None and not self.scale_active
                 and all(r.net.handle.n_in == 1 for r in self.runs))
 
     def _run_external(self, train, step0):
@@ -368,12 +401,23 @@ class _Program(object):
             return {}
         if "reset" in kinds:
             raise ValueError("fetch `reset` on its own (the reference runs it separately, DM/util.py:37)")
+        mt_kinds = set(k for k in kinds if ":" in k)
+        if mt_kinds:
+            out = {}
+            for ti in sorted(set(int(k.split(":")[1]) for k in mt_kinds)):
+                out.update(self.mt_tasks[ti].execute(set(k.split(":")[0] for k in mt_kinds if int(k.split(":")[1]) == ti), feed))
+            kinds = kinds - mt_kinds
+            if not kinds:
+                return out
+            out.update(self.execute(kinds, feed))
+            return out
         train = "step" in kinds
         commit = "update" in kinds
         step0 = self._step0(feed)
         T = self.T
         out = {}
-        if self.fused is not None:
+        self._apply_scale_feed(feed)
+        if self.fused is not None and not self.scale_active:
             fx = self._forward_fused(train, step0)
             if train:
                 for d in self.dtheta.values():
@@ -396,8 +440,9 @@ class _Program(object):
             out["loss"] = float(fx.sum().item())
         if "fx" in kinds:
             out["fx"] = float(fx[T].item())
+        used_fused = self.fused is not None and not self.scale_active
         if "x" in kinds:
-            xf = self.runs[0].x_work if self.fused is not None else self._Xw
+            xf = self.runs[0].x_work if used_fused else self._Xw
             out["x"] = [xf[self.var_off[j]:self.var_off[j] + (int(np.prod(v["shape"])) if v["shape"] else 1)]
                         .reshape(v["shape"]).cpu().numpy() for j, v in enumerate(self.variables)]
         self.last_fx = fx
@@ -408,7 +453,7 @@ class _Program(object):
                 _engine.adam_step(net.theta, self.dtheta[k], ad["m"], ad["v"], ad["k"], lr=self.learning_rate)
             out["step"] = None
         if commit:
-            if self.fused is not None:
+            if used_fused:
                 self.X.copy_(self.runs[0].x_work)
             else:
                 self.X.copy_(self._Xw)
@@ -421,6 +466,76 @@ class _Program(object):
             out["update"] = None
         return out
 
+
+
+class _MtTask(object):
+    """One imitation-learning ("mt") task (DM/meta_dm_train.py:421-499): the optimizer nets run over PRE-RECORDED
+    gradient sequences [T, N] with their own LSTM state; loss = sum_t 0.5 ||label_t - delta_t||^2 / N_total; its own
+    Adam slots on the shared theta (DM/meta_dm_train.py:549-553).  This is the fully fused regime: one forward-unroll
+    launch + one BPTT launch per subset, no optimizee in the loop."""
+
+    def __init__(self, prog, index):
+        self.prog, self.index = prog, index
+        T = prog.T
+        self.subsets = []
+        for key, subset in zip(prog.net_keys, prog.subsets):
+            runs = [r for r in prog.runs if r.key == key]
+            if len(runs) != 1:
+                raise NotImplementedError("imitation tasks need each net's variables contiguous in the arena")
+            r = runs[0]
+            h = r.net.handle
+            if h.n_in != 1:
+                raise NotImplementedError("imitation tasks are implemented for the L2O-DM nets")
+            sf = h.state_floats
+            self.subsets.append(dict(run=r, n=r.n, state=h.new_state(r.n, prog.device),
+                                     ckpt=torch.zeros((T + 1) * max(sf * r.n, 1), device=prog.device),
+                                     inp=Placeholder("mt{}_input_subset{}".format(index, len(self.subsets))),
+                                     lab=Placeholder("mt{}_label_subset{}".format(index, len(self.subsets)))))
+        self.n_total = sum(sb["n"] for sb in self.subsets)
+        self.adam = {k: dict(m=torch.zeros_like(net.theta), v=torch.zeros_like(net.theta), k=0)
+                     for k, net in prog.nets.items()}
+        self.il = torch.zeros(1, dtype=torch.float64, device=prog.device)
+
+    def _dev(self, arr, T, n):
+        t = torch.as_tensor(np.asarray(arr, dtype=np.float32)) if not torch.is_tensor(arr) else arr.float()
+        return t.reshape(T, n).to(self.prog.device).contiguous()
+
+    def execute(self, kinds, feed):
+        prog, T = self.prog, self.prog.T
+        if kinds == {"reset_mt"}:
+            for sb in self.subsets:
+                sb["state"].zero_()
+            return {}
+        train, commit = "step_mt" in kinds, "update_mt" in kinds
+        self.il.zero_()
+        if train:
+            for d in prog.dtheta.values():
+                d.zero_()
+        finals = []
+        for sb in self.subsets:
+            r, n = sb["run"], sb["n"]
+            h = r.net.handle
+            inp, lab = self._dev(feed[sb["inp"]], T, n), self._dev(feed[sb["lab"]], T, n)
+            work = sb["state"].clone()
+            h.unroll_fwd(r.net.theta, n, T, work, in_seq=inp, ckpt=sb["ckpt"] if train else None, labels=lab,
+                         imit_loss=self.il, n_total=self.n_total)
+            if train:
+                h.unroll_bwd(r.net.theta, n, T, inp, sb["ckpt"], prog.dtheta[r.key], labels=lab, n_total=self.n_total)
+            finals.append(work)
+        out = {}
+        if "loss_mt" in kinds:
+            out["loss_mt:%d" % self.index] = float(self.il.item())
+        if train:
+            for k, net in prog.nets.items():
+                ad = self.adam[k]
+                ad["k"] += 1
+                _engine.adam_step(net.theta, prog.dtheta[k], ad["m"], ad["v"], ad["k"], lr=prog.learning_rate)
+            out["step_mt:%d" % self.index] = None
+        if commit:
+            for sb, w in zip(self.subsets, finals):
+                sb["state"].copy_(w)
+            out["update_mt:%d" % self.index] = None
+        return out
 
 class MetaOptimizer(object):
     """Learning to learn (meta) optimizer (DM/meta.py:219-414)."""

@@ -8,17 +8,39 @@ import numpy as np
 from . import problems
 
 
-def run_epoch(sess, cost_op, ops, reset, num_unrolls, step=None, unroll_len=None):
-    """Runs one optimization epoch (DM/util.py:31-75; the random-scaling and imitation branches are
-    "next" rows)."""
+def run_epoch(sess, cost_op, ops, reset, num_unrolls,
+              scale=None, rd_scale=False, rd_scale_bound=3.0, assign_func=None, var_x=None,
+              step=None, unroll_len=None,
+              task_i=-1, data=None, label_pl=None, input_pl=None):
+    """Runs one optimization epoch (DM/util.py:31-75), including the random-scaling branch (:40-54) and the
+    imitation-task branch (:62-74)."""
     start = timer()
     sess.run(reset)
     cost = None
-    feed_dict = {}
-    for i in range(num_unrolls):
-        if step is not None:
-            feed_dict[step] = i * unroll_len + 1
-        cost = sess.run([cost_op] + list(ops), feed_dict=feed_dict)[0]
+    if task_i == -1:
+        if rd_scale:
+            assert scale is not None and var_x is not None and assign_func is not None
+            r_scale = [np.exp(np.random.uniform(-rd_scale_bound, rd_scale_bound, size=k.shape)).astype(np.float32)
+                       for k in var_x]
+            assign_func([v.value() / r for v, r in zip(var_x, r_scale)])
+            feed_dict = {p: v for p, v in zip(scale, r_scale)}
+        else:
+            feed_dict = {}
+        for i in range(num_unrolls):
+            if step is not None:
+                feed_dict[step] = i * unroll_len + 1
+            cost = sess.run([cost_op] + list(ops), feed_dict=feed_dict)[0]
+    else:
+        assert data is not None and input_pl is not None and label_pl is not None
+        feed_dict = {}
+        for ri in range(num_unrolls):
+            for pl, dat in zip(label_pl, data["labels"][ri]):
+                feed_dict[pl] = dat
+            for pl, dat in zip(input_pl, data["inputs"][ri]):
+                feed_dict[pl] = dat
+            if step is not None:
+                feed_dict[step] = ri * unroll_len + 1
+            cost = sess.run([cost_op] + list(ops), feed_dict=feed_dict)[0]
     return timer() - start, cost
 
 

@@ -242,3 +242,92 @@ def test_rnnprop_training_matches_oracle():
         assert abs(cost - float(res.fx[-1])) <= 1e-5 * abs(float(res.fx[-1]))
         assert rel_err(np.concatenate([a.reshape(-1) for a in xs]), res.x_final) <= REL_TOL
         assert rel_err(next(iter(prog.nets.values())).theta, tr.theta) <= 5e-5, it
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training-time surface (DM/meta_dm_train.py): scale placeholders + imitation ("mt") tasks + data generator
+# ---------------------------------------------------------------------------------------------------------------
+def _dm_train_setup(num_mt=1, T=6, lr=0.001):
+    from open_l2o_b200 import meta_dm_train, problems
+    problem = problems.quadratic(batch_size=16, num_dims=10)
+    optimizer = meta_dm_train.MetaOptimizer(num_mt, cw={"net": "CoordinateWiseDeepLSTM",
+                                                        "net_options": {"layers": (20, 20), "scale": 0.1}})
+    out = optimizer.meta_minimize(problem, T, learning_rate=lr)
+    return optimizer, out
+
+
+def test_imitation_task_matches_oracle():
+    """DM/meta_dm_train.py:463-480 + :549-553: two imitation unrolls (loss, state carry-over, per-task Adam)."""
+    from open_l2o_b200 import meta
+    T, lr = 6, 0.001
+    optimizer, (ms, scale, var_x, constants, subsets, loss_mt, steps_mt, update_mt, reset_mt, mt_labels, mt_inputs) = \
+        _dm_train_setup(1, T, lr)
+    prog = optimizer.program
+    n = prog.N
+    sess = meta.Session()
+    sess.run(ms.reset)
+    sess.run(reset_mt[0])
+    spec = orc.NetSpec(layers=(20, 20), scale=0.1)
+    theta = next(iter(prog.nets.values())).theta.cpu().clone()
+    m, v = torch.zeros_like(theta), torch.zeros_like(theta)
+    state = orc.initial_state(spec, n)
+    gen = torch.Generator().manual_seed(4)
+    for it in range(2):
+        inputs = torch.randn(T, n, generator=gen) * 0.3
+        labels = torch.randn(T, n, generator=gen) * 0.01
+        th = theta.clone().requires_grad_(True)
+        loss_ref, state_next, _ = orc.imitation_loss(spec, th, inputs, labels, state)
+        (g,) = torch.autograd.grad(loss_ref, th)
+        theta, m, v = orc.tf_adam_step(theta, g, m, v, it + 1, lr=lr)
+        state = tuple((h.detach(), c.detach()) for h, c in state_next)
+        cost = sess.run([loss_mt[0], update_mt[0], steps_mt[0]],
+                        feed_dict={mt_inputs[0][0]: inputs.numpy(), mt_labels[0][0]: labels.numpy()})[0]
+        assert abs(cost - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+        assert rel_err(next(iter(prog.nets.values())).theta, theta) <= 5e-5, it
+
+
+def test_scale_placeholders_random_scaling_trick():
+    """DM/meta_dm_train.py:336-338,384-385 + DM/util.py:40-54: fx = f(x*scale), g = scale * grad f(x*scale)."""
+    from open_l2o_b200 import meta
+    T = 5
+    optimizer, (ms, scale, var_x, *_rest) = _dm_train_setup(0, T)
+    prog = optimizer.program
+    sess = meta.Session()
+    sess.run(ms.reset)
+    w, y = prog.const_vals["w"].cpu(), prog.const_vals["y"].cpu()
+    x0 = prog.X.cpu().clone().reshape(16, 10)
+    r = torch.exp(torch.rand(16, 10) * 6 - 3)
+    spec = orc.NetSpec(layers=(20, 20), scale=0.1)
+    theta = next(iter(prog.nets.values())).theta.cpu().clone()
+    with torch.no_grad():
+        pass
+    res = orc.unroll(spec, theta, x0, orc.initial_state(spec, 160), lambda x: orc.quadratic_f(x * r, w, y), T)
+    cost, xs = sess.run([ms.fx, ms.x], feed_dict={scale[0]: r.numpy()})
+    assert abs(cost - float(res.fx[-1])) <= 1e-5 * abs(float(res.fx[-1]))
+    assert rel_err(xs[0], res.x_final.detach()) <= REL_TOL
+    assert var_x[0].shape == (16, 10) and var_x[0].value().shape == (16, 10)
+
+
+def test_data_loader_and_run_epoch_branches():
+    """DM/data_generator.py:71-124 shapes + DM/util.py:31-75 branches (random scaling, imitation task)."""
+    from open_l2o_b200 import meta, util
+    from open_l2o_b200.data_generator import data_loader
+    T = 4
+    optimizer, (ms, scale, var_x, constants, subsets, loss_mt, steps_mt, update_mt, reset_mt, mt_labels, mt_inputs) = \
+        _dm_train_setup(1, T)
+    prog = optimizer.program
+    sess = meta.Session()
+    dl = data_loader(prog, "adam,rmsprop,nag", T)
+    for task in range(3):
+        data = dl.get_data(task, sess, num_unrolls=2, assign_func=optimizer.assign_func, rd_scale_bound=3.0)
+        assert len(data["inputs"]) == 2 and data["inputs"][0][0].shape == (T, prog.N)
+        assert np.isfinite(data["labels"][1][0]).all() and np.abs(data["labels"][0][0]).max() > 0
+    # Adam's first move is lr * sign(g)
+    d0 = dl.get_data(0, sess, num_unrolls=1, if_scale=False)
+    assert np.allclose(np.abs(d0["labels"][0][0][0]), 0.01, atol=1e-4)
+    t, cost = util.run_epoch(sess, loss_mt[0], [update_mt[0], steps_mt[0]], reset_mt[0], 2, task_i=0, data=data,
+                             label_pl=mt_labels[0], input_pl=mt_inputs[0])
+    assert np.isfinite(cost)
+    t, cost = util.run_epoch(sess, ms.fx, [ms.update, ms.step], ms.reset, 2, scale=scale, rd_scale=True,
+                             assign_func=optimizer.assign_func, var_x=var_x)
+    assert np.isfinite(cost)
