@@ -86,6 +86,8 @@ typedef struct {
   float* x;             /* optional [n], x += delta */
   float* delta;         /* optional [n] */
   float* feat_out;      /* optional [2][n]: (m~, g~) actually fed to the net (recorded for BPTT) */
+  const int32_t* step_ptr; /* optional DEVICE scalar: when non-NULL, p = float(*step_ptr + t_offset) (CUDA-graph friendly) */
+  int32_t t_offset;
 } l2o_step_args;
 
 typedef struct {

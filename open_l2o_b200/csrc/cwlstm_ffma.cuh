@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(kTile) step_kernel(l2o_step_args a, NetRt rt) 
     if constexpr (C::NIN == 2) {
       if (a.m != nullptr) {
         float m = a.m[i], v = a.v[i];
-        adam_features(raw0, m, v, a.beta1, a.beta2, a.p, raw0, raw1);
+        const float p = a.step_ptr ? (float)(*a.step_ptr + a.t_offset) : a.p;
+        adam_features(raw0, m, v, a.beta1, a.beta2, p, raw0, raw1);
         a.m[i] = m; a.v[i] = v;
       } else {
         raw1 = a.in1[i];

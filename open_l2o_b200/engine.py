@@ -90,7 +90,7 @@ class NetHandle:
 
     # ---- kernels -------------------------------------------------------------------------
     def step(self, theta, in0, state_in, state_out, *, in1=None, m=None, v=None, beta1=0.95, beta2=0.95, p=1.0,
-             x=None, delta=None, feat_out=None):
+             x=None, delta=None, feat_out=None, step_ptr=None, t_offset=0):
         a = StepArgs()
         a.n = in0.numel()
         a.theta = _ptr(theta, name="theta")
@@ -99,6 +99,7 @@ class NetHandle:
         a.beta1, a.beta2, a.p = beta1, beta2, p
         a.state_in, a.state_out = _ptr(state_in, name="state_in"), _ptr(state_out, name="state_out")
         a.x, a.delta, a.feat_out = _ptr(x, name="x"), _ptr(delta, name="delta"), _ptr(feat_out, name="feat_out")
+        a.step_ptr, a.t_offset = _ptr(step_ptr, torch.int32, "step_ptr"), t_offset
         if theta.numel() != self.n_theta:
             raise L2OError(f"theta has {theta.numel()} elements, net needs {self.n_theta}")
         _lib.check(_lib.lib().l2o_step(self._h, C.byref(a), _stream()), "l2o_step")

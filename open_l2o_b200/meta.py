@@ -189,6 +189,7 @@ class _Program(object):
         # per-variable scale placeholders (random-scaling trick, DM/meta_dm_train.py:336-338,384-385): fx = f(x * scale)
         self.scale_placeholders = [Placeholder(v["name"] + "_scale") for v in self.variables]
         self.scale_flat = torch.ones(self.N, device=self.device)
+        self.step_dev = torch.ones(1, dtype=torch.int32, device=self.device)  # step0 of the current unroll (RNNProp)
         self.scale_active = False
         self.mt_tasks = []
         self.unroll_idx = 0
@@ -327,7 +328,7 @@ class _Program(object):
                 kw = {}
                 if h.n_in == 2:
                     kw = dict(m=r.m_work, v=r.v_work, beta1=self.opt.beta1, beta2=self.opt.beta2,
-                              p=float(step0 + t), feat_out=r.feat_rec[t])
+                              step_ptr=self.step_dev, t_offset=t, feat_out=r.feat_rec[t])
                 h.step(r.net.theta, r.g_rec[t], r.ckpt[t * slot:(t + 1) * slot], r.ckpt[(t + 1) * slot:(t + 2) * slot],
                        x=Xw[r.off:r.off + r.n], **kw)
         if train:
@@ -359,13 +360,14 @@ class _Program(object):
         return fx
 
     def _graph_eligible(self):
-        # RNNProp's bias-correction exponent p = step + t is a host scalar that changes every unroll -> stays eager
-        return (os.environ.get("L2O_CUDA_GRAPH", "1") != "0" and self.fused is None and not self.scale_active
-                and all(r.net.handle.n_in == 1 for r in self.runs))
+        # RNNProp's bias-correction exponent p = step0 + t is read from a device scalar (self.step_dev), so the graph
+        # stays valid from unroll to unroll
+        return os.environ.get("L2O_CUDA_GRAPH", "1") != "0" and self.fused is None and not self.scale_active
 
     def _run_external(self, train, step0):
         """Eager on the first two calls (warm-up: lazy allocations, autograd caches), then capture once per mode and
         replay: the per-step launches (~15 tiny kernels) collapse into one graph launch."""
+        self.step_dev.fill_(int(step0))
         key = bool(train)
         if not self._graph_eligible() or self._graph_failed:
             return self._graph_body(train, step0)
