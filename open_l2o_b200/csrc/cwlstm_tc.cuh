@@ -187,6 +187,27 @@ __device__ __forceinline__ float ext_weight(const float* __restrict__ theta, boo
   return 0.f;
 }
 
+// BPTT operand layout (cwlstm_tc_bwd.cuh): A row = [h1p (0..19) | features,1 (20..23) | h1n (24..43) | h2p (44..63)];
+// Z1 contracts columns [0,24), Z2 columns [16,64).  Value of the extended weight matrix at (row k of that
+// contraction range, interleaved gate column n).
+constexpr int kBColXC = 20, kBColH1N = 24, kBColH2P = 44, kBZ2Start = 16;
+template <class C>
+__device__ __forceinline__ float ext_weight_bwd(const float* __restrict__ theta, bool l2, int k, int n) {
+  const int u = n >> 2, g = n & 3;
+  const int col = g * kH + u;
+  if (!l2) {
+    if (k < kH) return theta[C::O_W1 + (C::F + k) * C::G1 + col];
+    if (k < kBColXC + C::F) return theta[C::O_W1 + (k - kBColXC) * C::G1 + col];
+    if (k == kBColXC + C::F) return theta[C::O_B1 + col];
+    return 0.f;
+  }
+  const int acol = kBZ2Start + k;  // A column
+  if (acol == kBColXC + C::F) return theta[C::O_B2 + col];
+  if (acol >= kBColH1N && acol < kBColH1N + 2 * kH) return theta[C::O_W2 + (acol - kBColH1N) * C::G2 + col];
+  return 0.f;
+}
+
+// mode 0: forward image (B1 | B2, hi/lo);  mode 1: BPTT image (B1' | B2' in the BPTT operand order, then T1 | T2)
 template <class C>
 __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __restrict__ img, int with_transposed) {
   static_assert(C::H1 == kH && C::H2 == kH && C::F <= 3 && !C::FC, "tc engine: LSTM-20x2, F <= 3");
@@ -206,7 +227,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
       const bool l2 = e >= kK1 * kN;
       const int ee = l2 ? e - kK1 * kN : e;
       const int k = ee / kN, n = ee % kN;
-      split_tf32(ext_weight<C>(theta, l2, k, n), hi, lo);
+      split_tf32(with_transposed ? ext_weight_bwd<C>(theta, l2, k, n) : ext_weight<C>(theta, l2, k, n), hi, lo);
       const int idx = img_index(k, n);
       (l2 ? b2h : b1h)[idx] = hi;
       (l2 ? b2l : b1l)[idx] = to_tf32(lo);
@@ -215,7 +236,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
       const bool l2 = e2 >= kT1Rows * kN;
       const int ee = l2 ? e2 - kT1Rows * kN : e2;
       const int k = ee / kN, n = ee % kN;  // k = input row (n'), n = gate (k')
-      const float w = (k < (l2 ? kK2 : kK1)) ? ext_weight<C>(theta, l2, k, n) : 0.f;
+      const float w = (k < (l2 ? kK2 : kK1)) ? ext_weight_bwd<C>(theta, l2, k, n) : 0.f;
       split_tf32(w, hi, lo);
       const int idx = timg_index(l2 ? kT2Rows : kT1Rows, k, n);
       (l2 ? t2h : t1h)[idx] = hi;

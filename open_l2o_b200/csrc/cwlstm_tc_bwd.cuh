@@ -19,13 +19,14 @@ using namespace tc;
 constexpr int kEpi = 256;
 constexpr int kThreadsB = kEpi + 128;
 constexpr int kEpiRegs = 224, kIssuerRegs = 40;
-// TMEM column map
-constexpr int cD1 = 0;                   // Z1 accumulators (kept until the layer-1 backward re-reads them)
+// TMEM column map.  The A operand of the gate recompute is ALIASED into the dZ operand region: it is dead once Z1/Z2
+// have completed (before dZ2 is written) and is rewritten only after the previous step's dX1 MMAs have drained.
+constexpr int cD1 = 0;                   // Z1 accumulators (read by the layer-1 backward phase)
 constexpr int cD2 = 80;                  // Z2 accumulators, then dX2 / dX1 results (aliased)
-constexpr int cAFh = 160, cAFl = 208;    // forward A rows [u | 1 | . | h1 | h2], hi / lo
-constexpr int cAZh = 256, cAZl = 336;    // dZ rows (80 gate columns), hi / lo
-constexpr int cW2 = 416;                 // dW2^T accumulator: lanes = gate rows, 48 feature columns
-constexpr int cW1 = 464;                 // dW1^T accumulator: 32 feature columns
+constexpr int cAZh = 160, cAZl = 240;    // dZ rows (80 gate columns), hi / lo
+constexpr int cAh = cAZh, cAl = cAZl;    // A rows [h1p | u,1 | h1n | h2p] (64 columns), hi / lo -- aliased
+constexpr int cW2 = 320;                 // dW2^T accumulator: lanes = gate rows, 48 feature columns
+constexpr int cW1 = 368;                 // dW1^T accumulator: 32 feature columns
 static_assert(cW1 + 32 <= kTmemCols, "TMEM budget");
 // Staged operand Y = [X (48 feature slots) | dZ (80 gate slots)] per coordinate, MN-major SWIZZLE_128B_BASE32B
 // (the only shared-memory layout the tensor core accepts for MN-major tf32; address map verified on the B200 with
@@ -52,7 +53,7 @@ struct SmemB {
   float y_lo[kYFloats];
   float img[kImgAllFloats];    // B1h|B1l|B2h|B2l (forward, K-major) | T1h|T1l|T2h|T2l (transposed, K-major)
   float wo[kH + 4];
-  uint64_t wbar, a_ready, d_ready, w_done, z_ready, f_ready;
+  uint64_t wbar, a_ready, d_ready, w_done;
   uint32_t tmem_slot, pad;
 };
 static_assert(sizeof(SmemB) + 1024 <= 227 * 1024, "shared memory budget");
@@ -138,47 +139,6 @@ __device__ __forceinline__ void unit_bwd(float* g, float cprev, float tcn, float
   dc = dcv * f;
 }
 
-// Feature/checkpoint phase of one step: loads the checkpointed rows, writes A_F = [u | 1 | h1p | h2p] to TMEM and
-// returns the values later phases need.  It depends only on the checkpoints, so the step loop runs it one step AHEAD
-// (right after the previous step's layer-1 backward) and its Z1 MMAs overlap the previous step's dW1 batch.
-template <class C, int HALF, int NU, int U0>
-__device__ __forceinline__ void feature_phase(const l2o_bwd_args& a, const NetRt& rt, bool act, int64_t i, int64_t n,
-                                              int64_t slot, int t, uint32_t tAFh, uint32_t tAFl, float* u4, float* h2p,
-                                              float* c1p, float* c2p) {
-  const float* ck = a.ckpt + (int64_t)t * slot;
-  {
-    const float raw0 = act ? a.in_seq[(int64_t)t * n + i] : 0.f;
-    float uu[C::F];
-    preprocess<C>(nullptr, rt, raw0, 0.f, uu);
-    u4[0] = u4[1] = u4[2] = u4[3] = 0.f;
-#pragma unroll
-    for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
-    u4[C::F] = 1.0f;
-  }
-  float h1p[NU];
-#pragma unroll
-  for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h2p[k] = 0.f; c1p[k] = 0.f; c2p[k] = 0.f; }
-  if (act) {  // all four checkpoint rows at once: one DRAM latency per step
-    load_vec<NU>(ck + i * kH + U0, h1p);
-    load_vec<NU>(ck + 2 * n * kH + i * kH + U0, h2p);
-    load_vec<NU>(ck + (n + i) * kH + U0, c1p);
-    load_vec<NU>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
-    if (t > 0) {  // pull the following step's rows towards L2
-      const float* nk = ck - slot;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + U0));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + U0));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + U0));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
-    }
-  }
-  if (HALF == 1) put4(tAFh, tAFl, 0, u4, nullptr, nullptr, 0, true, false);
-#pragma unroll
-  for (int g4 = 0; g4 < NU / 4; ++g4) {
-    put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
-    put4(tAFh, tAFl, kColH2 + U0 + 4 * g4, h2p + 4 * g4, nullptr, nullptr, 0, true, false);
-  }
-}
-
 template <class C, int HALF>
 __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt, SmemB& S, uint32_t tmem_base, int warp,
                                          int lane) {
@@ -187,25 +147,23 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
   const int q = warp & 3;
   const int c = q * 32 + lane;  // coordinate within the tile == TMEM lane
   const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-  const uint32_t tD1 = tl + cD1, tD2 = tl + cD2, tAFh = tl + cAFh, tAFl = tl + cAFl, tAZh = tl + cAZh, tAZl = tl + cAZl;
+  const uint32_t tD1 = tl + cD1, tD2 = tl + cD2, tAh = tl + cAh, tAl = tl + cAl, tAZh = tl + cAZh, tAZl = tl + cAZl;
   const int T = a.T;
   const int64_t n = a.n;
   const int64_t slot = n * C::SF;
   const int64_t ntiles = (n + 127) / 128;
-  uint32_t pd = 0, pz = 0;  // parities of d_ready (Z2, dX2, dX1 in turn) and z_ready (Z1)
-  int pi = 0;               // profile event index
+  uint32_t pd = 0;  // parity of d_ready (Z1+Z2, dX2, dX1 in turn)
+  int pi = 0;       // profile event index
   const bool prof = (q == 0 && lane == 0);
   (void)pi; (void)prof;
+  bool dx1_pending = false;  // a dX1 batch whose completion has not been consumed yet
   // w_done completes exactly twice per step: dW2 (even completion, parity 0) then dW1 (odd, parity 1)
   float acc_wo[NU], acc_bo = 0.f;
 #pragma unroll
   for (int k = 0; k < NU; ++k) acc_wo[k] = 0.f;
-  // zero the persistent dW accumulators (lane = gate row) and the A pad columns
-  if (HALF == 0) {
+  if (HALF == 0) {  // zero the persistent dW accumulators (lane = gate row)
 #pragma unroll
     for (int k = 0; k < (48 + 32) / 4; ++k) tmem_st4(tl + cW2 + 4 * k, 0.f, 0.f, 0.f, 0.f);
-    tmem_st4(tAFh + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);  // A pad columns 44..47: zero weights, must be finite
-    tmem_st4(tAFl + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
   }
   tc_wait_st();
 
@@ -216,41 +174,67 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 #pragma unroll
     for (int k = 0; k < NU; ++k) { dh1c[k] = 0.f; dc1c[k] = 0.f; dh2c[k] = 0.f; dc2c[k] = 0.f; }
     float lam = act ? a.g_rec[(int64_t)T * n + i] : 0.f;
-    // prologue: feature phase of the first (last-in-time) step of this tile
-    float u4[4], h2p[NU], c1p[NU], c2p[NU];
-    feature_phase<C, HALF, NU, U0>(a, rt, act, i, n, slot, T - 1, tAFh, tAFl, u4, h2p, c1p, c2p);
-    tc_wait_st();
-    tc_fence_before();
-    mbar_arrive(&S.f_ready);
 
     for (int t = T - 1; t >= 0; --t) {
       const float* ck = a.ckpt + (int64_t)t * slot;
+      // ---------------- P0: checkpoint rows -> A = [h1p | u,1 | h1n | h2p] ----------------
+      // h1n(t), the layer-1 output of step t, IS the checkpointed h1 of slot t+1: no layer-1 recompute is needed to
+      // form the layer-2 input, so Z1 and Z2 are issued back to back.  Loads go out before the dX1 wait.
+      float u4[4] = {0.f, 0.f, 0.f, 0.f};
+      float h1p[NU], h1n[NU], h2p[NU], c1p[NU], c2p[NU];
+      {
+        const float raw0 = act ? a.in_seq[(int64_t)t * n + i] : 0.f;
+        float uu[C::F];
+        preprocess<C>(nullptr, rt, raw0, 0.f, uu);
+#pragma unroll
+        for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
+        u4[C::F] = 1.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h1n[k] = 0.f; h2p[k] = 0.f; c1p[k] = 0.f; c2p[k] = 0.f; }
+      if (act) {
+        load_vec<NU>(ck + i * kH + U0, h1p);
+        load_vec<NU>(ck + slot + i * kH + U0, h1n);
+        load_vec<NU>(ck + 2 * n * kH + i * kH + U0, h2p);
+        load_vec<NU>(ck + (n + i) * kH + U0, c1p);
+        load_vec<NU>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
+        if (t > 0) {  // pull the following step's rows towards L2
+          const float* nk = ck - slot;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + U0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + U0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + U0));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
+        }
+      }
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      // ---------------- P1: h1n = LSTM1 forward (only what layer 2 needs) ----------------
-      float h1n[NU];
-      mbar_wait(&S.z_ready, pz);
-      pz ^= 1;
-      tc_fence_after();
+      if (dx1_pending) {  // previous step's dX1 = dZ1 . W1^T : carries, and the dZ operand region becomes free
+        mbar_wait(&S.d_ready, pd);
+        pd ^= 1;
+        tc_fence_after();
+        dx1_pending = false;
+        if (t != T - 1) {
+#pragma unroll
+          for (int g4 = 0; g4 < NU / 4; ++g4) {
+            float v[4];
+            tmem_ld4(tD2 + U0 + 4 * g4, v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dh1c[4 * g4 + u] = v[u];
+          }
+        }
+      }
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
+      if (HALF == 1) put4(tAh, tAl, kBColXC, u4, nullptr, nullptr, 0, true, false);
 #pragma unroll
       for (int g4 = 0; g4 < NU / 4; ++g4) {
-        float z[16], g[16];
-        tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
-        gates4(z, g);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float cn = fmaf(g[4 * u + 2], c1p[4 * g4 + u], g[4 * u + 0] * g[4 * u + 1]);
-          h1n[4 * g4 + u] = tanh_fast(cn) * g[4 * u + 3];
-          // park the ACTIVATED gates in the Z1 accumulator columns: the layer-1 backward phase reads them back
-          tmem_st4(tD1 + 4 * U0 + 16 * g4 + 4 * u, g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
-        }
-        put4(tAFh, tAFl, kColH1 + U0 + 4 * g4, h1n + 4 * g4, nullptr, nullptr, 0, true, false);
+        put4(tAh, tAl, U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
+        put4(tAh, tAl, kBColH1N + U0 + 4 * g4, h1n + 4 * g4, nullptr, nullptr, 0, true, false);
+        put4(tAh, tAl, kBColH2P + U0 + 4 * g4, h2p + 4 * g4, nullptr, nullptr, 0, true, false);
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready);
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      // ---------------- P2: layer-2 forward recompute + output layer + layer-2 backward ----------------
+      // ---------------- P2: layer-2 gates + output layer + layer-2 backward ----------------
       mbar_wait(&S.d_ready, pd);
       pd ^= 1;
       tc_fence_after();
@@ -279,16 +263,12 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
             put4(tAZh, tAZl, 4 * (U0 + k), g + 4 * u, S.y_hi, S.y_lo, dz_sidx(c, U0 + k), true, true);
           }
         }
-        // X2 row = [0.. 1 .. | h1n | h2p]
-        if (HALF == 1) {
-          float x0[4] = {0.f, 0.f, 0.f, 0.f};
-          x0[C::F] = 1.0f;
-          put4(0, 0, 0, x0, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
-        }
+        // X2 row = A columns 16..63 = [h1p tail (unused) | u,1 | h1n | h2p]  (slot = column - 16)
+        if (HALF == 1) put4(0, 0, 0, u4, S.y_hi, S.y_lo, x_sidx(c, (kBColXC - kBZ2Start) / 4), false, true);
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
-          put4(0, 0, 0, h1n + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
-          put4(0, 0, 0, h2p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH2 + U0) / 4 + g4), false, true);
+          put4(0, 0, 0, h1n + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kBColH1N - kBZ2Start + U0) / 4 + g4), false, true);
+          put4(0, 0, 0, h2p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kBColH2P - kBZ2Start + U0) / 4 + g4), false, true);
         }
       }
       fence_proxy_async();
@@ -303,25 +283,24 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
       float dh1[NU];
 #pragma unroll
-      for (int g4 = 0; g4 < NU / 4; ++g4) {
+      for (int g4 = 0; g4 < NU / 4; ++g4) {  // dX2 columns are in Z2 contraction order: 8.. = h1n, 28.. = h2p
         float v[4];
-        tmem_ld4(tD2 + kColH1 + U0 + 4 * g4, v);
+        tmem_ld4(tD2 + (kBColH1N - kBZ2Start) + U0 + 4 * g4, v);
 #pragma unroll
         for (int u = 0; u < 4; ++u) dh1[4 * g4 + u] = v[u] + dh1c[4 * g4 + u];
-        tmem_ld4(tD2 + kColH2 + U0 + 4 * g4, v);
+        tmem_ld4(tD2 + (kBColH2P - kBZ2Start) + U0 + 4 * g4, v);
 #pragma unroll
         for (int u = 0; u < 4; ++u) dh2c[4 * g4 + u] = v[u];
       }
       {
         // compute dz1 and feed the dX1 A operand (TMEM) first; the shared staging is touched only after the dW2 MMAs
         // have drained, so their ~2K cycles overlap with this phase's arithmetic instead of stalling it
-        float h1p[NU], dz1[4 * NU];
-#pragma unroll
-        for (int k = 0; k < NU; ++k) h1p[k] = 0.f;
-        if (act) load_vec<NU>(ck + i * kH + U0, h1p);  // re-read (cache hit): cheaper than 12 live registers
+        float dz1[4 * NU];
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
-          tmem_ld16(tD1 + 4 * U0 + 16 * g4, dz1 + 16 * g4);  // activated gates parked by P1
+          float z[16];
+          tmem_ld16(tD1 + 4 * U0 + 16 * g4, z);
+          gates4(z, dz1 + 16 * g4);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int k = 4 * g4 + u;
@@ -334,42 +313,28 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
         }
         mbar_wait(&S.w_done, 0);  // dW2 MMAs done: staging may be overwritten
         if (prof) { L2O_PROF(HALF, pi); ++pi; }
+        // X1 row = A columns 0..23 = [h1p | u,1]
 #pragma unroll
         for (int g4 = 0; g4 < NU / 4; ++g4) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             put4(0, 0, 0, dz1 + 16 * g4 + 4 * u, S.y_hi, S.y_lo, dz_sidx(c, U0 + 4 * g4 + u), false, true);
-          put4(0, 0, 0, h1p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, (kColH1 + U0) / 4 + g4), false, true);
+          put4(0, 0, 0, h1p + 4 * g4, S.y_hi, S.y_lo, x_sidx(c, U0 / 4 + g4), false, true);
         }
-        if (HALF == 1) put4(0, 0, 0, u4, S.y_hi, S.y_lo, x_sidx(c, 0), false, true);
+        if (HALF == 1) put4(0, 0, 0, u4, S.y_hi, S.y_lo, x_sidx(c, kBColXC / 4), false, true);
       }
       fence_proxy_async();
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready);
+      dx1_pending = true;
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      // ---------------- P0 of the NEXT step (t-1), one step ahead: its Z1 MMAs are issued before this step's dW1 ----
       if (act) lam += a.g_rec[(int64_t)t * n + i];
-      if (t > 0) {
-        feature_phase<C, HALF, NU, U0>(a, rt, act, i, n, slot, t - 1, tAFh, tAFl, u4, h2p, c1p, c2p);
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&S.f_ready);
-      }
-      if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      // ---------------- P4: carry for step t-1 ----------------
-      mbar_wait(&S.d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
-      if (prof) { L2O_PROF(HALF, pi); ++pi; }
-#pragma unroll
-      for (int g4 = 0; g4 < NU / 4; ++g4) {
-        float v[4];
-        tmem_ld4(tD2 + kColH1 + U0 + 4 * g4, v);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dh1c[4 * g4 + u] = v[u];
-      }
     }
+  }
+  if (dx1_pending) {  // drain the last dX1 completion so the barrier phase bookkeeping stays consistent
+    mbar_wait(&S.d_ready, pd);
+    pd ^= 1;
   }
   // ---------------- flush: output-layer gradient from registers ----------------
 #pragma unroll
@@ -399,9 +364,10 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = 4 * k4 + e;
-          int idx = -1;
-          if (k == C::F) idx = C::O_B2 + col;
-          else if (k >= kColH1 && k < kColH1 + 2 * kH) idx = C::O_W2 + (k - kColH1) * C::G2 + col;
+          int idx = -1;  // slot k <-> A column kBZ2Start + k
+          const int acol = kBZ2Start + k;
+          if (acol == kBColXC + C::F) idx = C::O_B2 + col;
+          else if (acol >= kBColH1N && acol < kBColH1N + 2 * kH) idx = C::O_W2 + (acol - kBColH1N) * C::G2 + col;
           if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
         }
       }
@@ -414,10 +380,10 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = 4 * k4 + e;
-          int idx = -1;
-          if (k < C::F) idx = C::O_W1 + k * C::G1 + col;
-          else if (k == C::F) idx = C::O_B1 + col;
-          else if (k >= kColH1 && k < kColH1 + kH) idx = C::O_W1 + (C::F + k - kColH1) * C::G1 + col;
+          int idx = -1;  // slot k <-> A column k
+          if (k < kH) idx = C::O_W1 + (C::F + k) * C::G1 + col;
+          else if (k < kBColXC + C::F) idx = C::O_W1 + (k - kBColXC) * C::G1 + col;
+          else if (k == kBColXC + C::F) idx = C::O_B1 + col;
           if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
         }
       }
@@ -441,8 +407,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
       mbar_init(&S.a_ready, kEpi);
       mbar_init(&S.d_ready, 1);
       mbar_init(&S.w_done, 1);
-      mbar_init(&S.z_ready, 1);
-      mbar_init(&S.f_ready, kEpi);
       fence_barrier_init();
     }
     __syncwarp();
@@ -487,38 +451,28 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
       constexpr uint64_t kFwdStep = (2 * kLBO) >> 4;      // K-major: 8 k = two 16-byte chunks
       constexpr uint64_t kT1Step = (2 * kT1LBO) >> 4, kT2Step = (2 * kT2LBO) >> 4;  // 8 gates = two 16-byte chunks
       constexpr uint64_t kYStep = (2 * kYSBO) >> 4;       // 8 coordinates = two K atoms
-      const uint32_t tD1 = tmem_base + cD1, tD2 = tmem_base + cD2, tAFh = tmem_base + cAFh, tAFl = tmem_base + cAFl;
+      const uint32_t tD1 = tmem_base + cD1, tD2 = tmem_base + cD2, tAh = tmem_base + cAh, tAl = tmem_base + cAl;
       const uint32_t tAZh = tmem_base + cAZh, tAZl = tmem_base + cAZl, tW2 = tmem_base + cW2, tW1 = tmem_base + cW1;
-      uint32_t pa = 0, pf = 0;
+      uint32_t pa = 0;
       int pi = 0;
       (void)pi;
-      // Z1 of one step: waits for the feature phase (f_ready), signals z_ready
-      auto issue_z1 = [&]() {
-        mbar_wait(&S.f_ready, pf); pf ^= 1; tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int kc = 0; kc < kK1 / 8; ++kc) {
-            mma_tf32_ts(tD1, tAFl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
-            mma_tf32_ts(tD1, tAFh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
-            mma_tf32_ts(tD1, tAFh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
-          }
-          tc_commit(&S.z_ready);
-        }
-        __syncwarp();
-      };
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        issue_z1();  // tile prologue
-        L2O_PROF(2, pi); ++pi;
         for (int t = T - 1; t >= 0; --t) {
-          // Z2
+          // Z1 = A[0:24].B1'  and  Z2 = A[16:64].B2'  back to back (both depend only on checkpointed rows)
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
           L2O_PROF(2, pi); ++pi;
           if (elect_one()) {
 #pragma unroll
+            for (int kc = 0; kc < kK1 / 8; ++kc) {
+              mma_tf32_ts(tD1, tAl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+              mma_tf32_ts(tD1, tAh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
+              mma_tf32_ts(tD1, tAh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
+            }
+#pragma unroll
             for (int kc = 0; kc < kK2 / 8; ++kc) {
-              mma_tf32_ts(tD2, tAFl + 8 * kc, b2h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
-              mma_tf32_ts(tD2, tAFh + 8 * kc, b2l + kc * kFwdStep, id_fwd, 1u);
-              mma_tf32_ts(tD2, tAFh + 8 * kc, b2h + kc * kFwdStep, id_fwd, 1u);
+              mma_tf32_ts(tD2, tAl + kBZ2Start + 8 * kc, b2h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+              mma_tf32_ts(tD2, tAh + kBZ2Start + 8 * kc, b2l + kc * kFwdStep, id_fwd, 1u);
+              mma_tf32_ts(tD2, tAh + kBZ2Start + 8 * kc, b2h + kc * kFwdStep, id_fwd, 1u);
             }
             tc_commit(&S.d_ready);
           }
@@ -549,7 +503,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
           }
           __syncwarp();
           L2O_PROF(2, pi); ++pi;
-          // dX1 = dZ1 . W1^T
+          // dX1 = dZ1 . W1^T   and   dW1^T += dZ1^T . X1
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
           L2O_PROF(2, pi); ++pi;
           if (elect_one()) {
@@ -563,10 +517,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
           }
           __syncwarp();
           L2O_PROF(2, pi); ++pi;
-          // Z1 of the NEXT step goes ahead of this step's (long, off-critical-path) dW1 batch
-          if (t > 0) issue_z1();
-          L2O_PROF(2, pi); ++pi;
-          // dW1^T += dZ1^T . X1
           if (elect_one()) {
 #pragma unroll
             for (int kb = 0; kb < 16; ++kb) {
