@@ -182,16 +182,10 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       // form the layer-2 input, so Z1 and Z2 are issued back to back.  Loads go out before the dX1 wait.
       float u4[4] = {0.f, 0.f, 0.f, 0.f};
       float h1p[NU], h1n[NU], h2p[NU], c1p[NU], c2p[NU];
-      {
-        const float raw0 = act ? a.in_seq[(int64_t)t * n + i] : 0.f;
-        float uu[C::F];
-        preprocess<C>(nullptr, rt, raw0, 0.f, uu);
-#pragma unroll
-        for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
-        u4[C::F] = 1.0f;
-      }
 #pragma unroll
       for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h1n[k] = 0.f; h2p[k] = 0.f; c1p[k] = 0.f; c2p[k] = 0.f; }
+      float raw0 = 0.f;
+      if (HALF == 1 && act) raw0 = a.in_seq[(int64_t)t * n + i];  // only half 1 owns the feature chunk
       if (act) {
         load_vec<NU>(ck + i * kH + U0, h1p);
         load_vec<NU>(ck + slot + i * kH + U0, h1n);
@@ -204,7 +198,18 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + U0));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + U0));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
+          if (HALF == 1) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_seq + (int64_t)(t - 1) * n + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.g_rec + (int64_t)(t - 1) * n + i));
+          }
         }
+      }
+      if (HALF == 1) {
+        float uu[C::F];
+        preprocess<C>(nullptr, rt, raw0, 0.f, uu);
+#pragma unroll
+        for (int k = 0; k < C::F; ++k) u4[k] = uu[k];
+        u4[C::F] = 1.0f;
       }
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
       if (dx1_pending) {  // previous step's dX1 = dZ1 . W1^T : carries, and the dZ operand region becomes free

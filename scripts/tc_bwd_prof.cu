@@ -25,24 +25,24 @@ int main() {
   }
   std::vector<long long> p(3 * 2048);
   cudaMemcpyFromSymbol(p.data(), tcb::g_prof, sizeof(long long) * 3 * 2048);
-  const char* en[12] = {"P0 done(loads+A_F st)", "arrived", "Z1 ready", "P1 arrived", "Z2 ready", "w_done(dW1 prev)", "P2 arrived", "dX2 ready",
-                        "w_done(dW2)", "P3 arrived", "dX1 ready", ""};
+  const char* en[9] = {"loads issued", "dX1(prev) ready+carry", "P0 arrived", "Z1Z2 ready", "w_done(dW1 prev)", "P2 arrived",
+                       "dX2 ready", "w_done(dW2)", "P3 arrived"};
   for (int role = 0; role < 2; ++role) {
-    printf("== epilogue half %d (warp q=0 lane 0): cycles since previous event, steps 2..5 of tile 0\n", role);
-    for (int st = 2; st < 6; ++st) {
+    printf("== epilogue half %d (warp q=0 lane 0): cycles since previous event, steps 2..4 of tile 0\n", role);
+    for (int st = 2; st < 5; ++st) {
       printf(" step %d:", st);
-      for (int e = 0; e < 11; ++e) {
-        const int idx = st * 11 + e;
+      for (int e = 0; e < 9; ++e) {
+        const int idx = st * 9 + e;
         printf(" %s=%lld", en[e], p[role * 2048 + idx] - p[role * 2048 + idx - 1]);
       }
-      printf("  | step total %lld\n", p[role * 2048 + st * 11 + 10] - p[role * 2048 + (st - 1) * 11 + 10]);
+      printf("  | step total %lld\n", p[role * 2048 + st * 9 + 8] - p[role * 2048 + (st - 1) * 9 + 8]);
     }
   }
-  const char* in[10] = {"a_ready(P0)", "Z1 issued", "a_ready(P1)", "Z2 issued", "a_ready(P2)", "dX2 issued", "dW2 issued", "a_ready(P3)", "dX1 issued", "dW1 issued"};
+  const char* in[8] = {"a_ready(P0)", "Z1Z2 issued", "a_ready(P2)", "dX2 issued", "dW2 issued", "a_ready(P3)", "dX1 issued", "dW1 issued"};
   printf("== issuer: cycles since previous event\n");
-  for (int st = 2; st < 6; ++st) {
+  for (int st = 2; st < 5; ++st) {
     printf(" step %d:", st);
-    for (int e = 0; e < 10; ++e) { const int idx = st * 10 + e; printf(" %s=%lld", in[e], p[2 * 2048 + idx] - p[2 * 2048 + idx - 1]); }
+    for (int e = 0; e < 8; ++e) { const int idx = st * 8 + e; printf(" %s=%lld", in[e], p[2 * 2048 + idx] - p[2 * 2048 + idx - 1]); }
     printf("\n");
   }
   return 0;
