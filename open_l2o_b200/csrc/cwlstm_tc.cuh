@@ -145,9 +145,20 @@ __device__ __forceinline__ float to_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// Error-compensated operand split for 3xTF32: the tensor core reads only the top 19 bits of an fp32 operand (sign,
+// 8 exponent, 10 mantissa bits — it truncates, verified on B200: passing x itself gives bit-identical results to
+// passing the explicitly truncated x), so the "hi" operand is x as is and lo = x - trunc19(x) (exact in fp32,
+// |lo| < 2^-10 |x|; its own truncation leaves a 2^-21 relative residual).  2 instructions per value instead of the 5
+// of cvt.rna.tf32.f32 + subtract.  Measured error of d-theta after T=100 against the fp64 oracle: 7.9e-7 (rna
+// split: 5.2e-7; the fp32 oracle itself: 9.7e-7).  -DL2O_SPLIT_RNA restores round-to-nearest for the hi part.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = to_tf32(x);
-  lo = x - hi;  // exact in fp32; the tensor core keeps its top 19 bits
+#if defined(L2O_SPLIT_RNA)
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+#else
+  hi = x;
+  lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+#endif
 }
 
 // instruction descriptor: D=f32, A=B=tf32, both K-major, N, M=128 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
@@ -227,7 +238,9 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
       const bool l2 = e >= kK1 * kN;
       const int ee = l2 ? e - kK1 * kN : e;
       const int k = ee / kN, n = ee % kN;
-      split_tf32(with_transposed ? ext_weight_bwd<C>(theta, l2, k, n) : ext_weight<C>(theta, l2, k, n), hi, lo);
+      const float w = with_transposed ? ext_weight_bwd<C>(theta, l2, k, n) : ext_weight<C>(theta, l2, k, n);
+      hi = to_tf32(w);
+      lo = w - hi;
       const int idx = img_index(k, n);
       (l2 ? b2h : b1h)[idx] = hi;
       (l2 ? b2l : b1l)[idx] = to_tf32(lo);
@@ -237,7 +250,8 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
       const int ee = l2 ? e2 - kT1Rows * kN : e2;
       const int k = ee / kN, n = ee % kN;  // k = input row (n'), n = gate (k')
       const float w = (k < (l2 ? kK2 : kK1)) ? ext_weight_bwd<C>(theta, l2, k, n) : 0.f;
-      split_tf32(w, hi, lo);
+      hi = to_tf32(w);
+      lo = w - hi;
       const int idx = timg_index(l2 ? kT2Rows : kT1Rows, k, n);
       (l2 ? t2h : t1h)[idx] = hi;
       (l2 ? t2l : t1l)[idx] = to_tf32(lo);
@@ -246,18 +260,36 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
 }
 
 // ------------------------------------------------------------------ epilogue helpers
+// One LSTM unit, pointwise.  Default form: 8 MUFU ops (5 ex2 + 3 rcp) instead of the 10 of five separate
+// sigmoid/tanh evaluations — sigma(i)*tanh(j) = (1-Ej) / ((1+Ei)(1+Ej)) and tanh(c')*sigma(o) likewise share one
+// reciprocal.  The exponents are clamped to 2^63 so the shared denominator stays finite (sigma/tanh are saturated to
+// fp32 precision long before that).  The activation pipe is the forward kernel's busiest unit (ncu: XU 50 %).
+__device__ __forceinline__ void lstm_point_fwd(float zi, float zj, float zf, float zo, float& c, float& h) {
+#ifdef L2O_FWD_MUFU10
+  const float i = sigmoid_fast(zi);
+  const float j = tanh_fast(zj);
+  const float f = sigmoid_fast(zf + 1.0f);
+  const float o = sigmoid_fast(zo);
+  const float cn = fmaf(f, c, i * j);
+  c = cn;
+  h = tanh_fast(cn) * o;
+#else
+  constexpr float kL = 1.4426950408889634f;
+  const float Ei = ex2_approx(fminf(-kL * zi, 63.f));
+  const float Ej = ex2_approx(fminf(-2.f * kL * zj, 63.f));
+  const float f = rcp_approx(1.0f + ex2_approx(fmaf(-kL, zf, -kL)));
+  const float ij = (1.0f - Ej) * rcp_approx((1.0f + Ei) * (1.0f + Ej));
+  const float cn = fmaf(f, c, ij);
+  c = cn;
+  const float Ec = ex2_approx(fminf(-2.f * kL * cn, 63.f));
+  const float Eo = ex2_approx(fminf(-kL * zo, 63.f));
+  h = (1.0f - Ec) * rcp_approx((1.0f + Ec) * (1.0f + Eo));
+#endif
+}
 // LSTM pointwise update of 4 hidden units from 16 accumulator columns (i,j,f,o interleaved).
 __device__ __forceinline__ void lstm_units4(const float* z, float* c, float* h) {
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const float i = sigmoid_fast(z[4 * u + 0]);
-    const float j = tanh_fast(z[4 * u + 1]);
-    const float f = sigmoid_fast(z[4 * u + 2] + 1.0f);
-    const float o = sigmoid_fast(z[4 * u + 3]);
-    const float cn = fmaf(f, c[u], i * j);
-    c[u] = cn;
-    h[u] = tanh_fast(cn) * o;
-  }
+  for (int u = 0; u < 4; ++u) lstm_point_fwd(z[4 * u + 0], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3], c[u], h[u]);
 }
 
 // write 4 values (hi/lo split) to A_hi / A_lo columns [col, col+4)
@@ -272,13 +304,7 @@ __device__ __forceinline__ void st_split4(uint32_t a_hi, uint32_t a_lo, int col,
 }
 
 __device__ __forceinline__ void lstm_unit_fwd(const float* z, float& c, float& h) {
-  const float i = sigmoid_fast(z[0]);
-  const float j = tanh_fast(z[1]);
-  const float f = sigmoid_fast(z[2] + 1.0f);
-  const float o = sigmoid_fast(z[3]);
-  const float cn = fmaf(f, c, i * j);
-  c = cn;
-  h = tanh_fast(cn) * o;
+  lstm_point_fwd(z[0], z[1], z[2], z[3], c, h);
 }
 
 struct Smem {

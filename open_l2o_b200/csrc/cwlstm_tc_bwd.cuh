@@ -130,12 +130,12 @@ __device__ __forceinline__ void gates4(const float* z, float* g) {
 // LSTM pointwise backward for one unit; g = (i, j, f, o) -> overwritten with (dz_i, dz_j, dz_f, dz_o)
 __device__ __forceinline__ void unit_bwd(float* g, float cprev, float tcn, float dh, float& dc) {
   const float i = g[0], j = g[1], f = g[2], o = g[3];
-  const float d_o = dh * tcn;
-  const float dcv = fmaf(dh * o, 1.0f - tcn * tcn, dc);
-  g[0] = dcv * j * i * (1.0f - i);
-  g[1] = dcv * i * (1.0f - j * j);
-  g[2] = dcv * cprev * f * (1.0f - f);
-  g[3] = d_o * o * (1.0f - o);
+  const float dho = dh * o;
+  const float dcv = fmaf(dho, fmaf(-tcn, tcn, 1.0f), dc);
+  g[0] = (dcv * j) * fmaf(-i, i, i);           // sigma' = i - i^2
+  g[1] = (dcv * i) * fmaf(-j, j, 1.0f);        // tanh'  = 1 - j^2
+  g[2] = (dcv * cprev) * fmaf(-f, f, f);
+  g[3] = (dho * tcn) * (1.0f - o);             // dh tcn o (1 - o)
   dc = dcv * f;
 }
 
