@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--unroll", type=int, default=0, help="T (0 = workload default)")
     ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other BASELINE configs (N=1 default run)")
     ap.add_argument("--cpu-sample-coords", type=int, default=8192)
     return ap.parse_args()
 
@@ -128,6 +129,45 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(use[0][1])), "reasons": sorted(reasons),
                 "samples": len(sm), "samples_in_timed_region": len(inside)}
+
+
+def quick_measure(workload, steps, warmup):
+    """Short device-resident train-mode measurement of another BASELINE config through the same public surface
+    (MetaOptimizer.meta_minimize + Session.run([fx, update, step])); reported under "also" at N=1."""
+    from open_l2o_b200 import engine as eng, meta
+    desc, coords, T, _ = WORKLOADS[workload]
+    problem, net_config, flavour = make_problem(workload, coords, 0)
+    cls = meta.RNNpropMetaOptimizer if flavour == "rnnprop" else meta.MetaOptimizer
+    optimizer = cls(seed=0, **net_config)
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, "w")
+    try:
+        ms = optimizer.meta_minimize(problem, T, learning_rate=0.001)
+    finally:
+        sys.stdout = _stdout
+    prog = optimizer.program
+    sess = meta.Session()
+    sess.run(ms.reset)
+    fetch = [ms.fx, ms.update, ms.step]
+    for _ in range(warmup):
+        sess.run(fetch)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        cost = sess.run(fetch)[0]
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 1e3
+    out = {"workload": desc, "coords": prog.N, "unroll": T, "mode": "train (fwd+BPTT+Adam)",
+           "regime": "fused" if prog.fused is not None else "external-gradient (torch autograd between step kernels, "
+           "one captured CUDA graph per unroll)", "value": prog.N * T * steps / t, "unit": "coordinate-updates/s",
+           "ms_per_step": 1e3 * t / steps, "steps": steps, "warmup": warmup,
+           "gpu_launches": int(eng.launch_count() - l0), "last_fx": cost}
+    del sess, ms, prog, optimizer, problem
+    torch.cuda.empty_cache()
+    return out
 
 
 def pick_cpu_threads():
@@ -304,6 +344,27 @@ def main():
                 "notes": "fp32 parity => 3xTF32 (tf32 = 1/2 bf16 rate): a 100%-busy tensor pipe reads 1/6 of this peak; "
                          "the activation pipe (~360 MUFU ops per coordinate-update) caps the path near 1.1e10 upd/s/GPU"}
 
+    # ---- infer mode (evaluate_dm.py: forward unroll only, no checkpoints) -----------------------------
+    infer = None
+    if prog.fused is not None:
+        ts = []
+        for _ in range(max(2, min(args.steps, 3))):
+            xw = prog.X.clone()
+            st = r.state.clone()
+            kf0.record()
+            h.unroll_fwd(r.net.theta, r.n, T, st, opt_kind=eng.OPT_KINDS[prog.fused.kind],
+                         opt_a=prog.const_vals[prog.fused.a], opt_b=prog.const_vals[prog.fused.b],
+                         opt_alpha=prog.fused.alpha, opt_fscale=prog.fused.fscale, x=xw, fx=prog.fx_buf)
+            kf1.record()
+            torch.cuda.synchronize()
+            ts.append(kf0.elapsed_time(kf1) / 1e3)
+        t_i = sum(ts) / len(ts)
+        ti = torch.tensor([t_i], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+        infer = {"value": coords * world * T / float(ti.item()), "unit": "coordinate-updates/s", "ms_per_unroll": 1e3 * t_i,
+                 "mode": "infer (forward unroll only, state on-chip, no checkpoint writes; l2o_unroll_fwd)"}
+
     # ---- end-to-end through the public API with HOST buffers ------------------------------------
     e2e = None
     if prog.fused is not None:
@@ -345,6 +406,15 @@ def main():
                "sample": "%d coordinates x T=%d separable-Rastrigin train unroll (fwd+autograd BPTT+Adam), torch-CPU "
                          "oracle, %d timed unrolls after 1 warm-up" % (n_s, T, len(ts))}
 
+    also = None
+    if rank == 0 and world == 1 and args.workload == "rastrigin" and not args.no_also:
+        also = []
+        for w in ("mlp", "lasso", "rnnprop_mlp", "quadratic"):
+            try:
+                also.append(quick_measure(w, steps=max(args.steps, 5), warmup=max(args.warmup, 3)))
+            except Exception as ex:  # the headline line must survive a failure of a side measurement
+                also.append({"workload": WORKLOADS[w][0], "error": repr(ex)[:200]})
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "coordinate-updates/s", "n_gpus": world, "steps": args.steps,
@@ -356,7 +426,7 @@ def main():
                        "l2_policy": "working set (checkpoints %.1f GB/GPU) >> 126 MB L2" % (r.ckpt.numel() * 4 / 1e9),
                        "last_fx": cost},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "infer": infer, "also": also,
         }
         print(json.dumps(line))
     if distributed:

@@ -8,6 +8,7 @@
  *   l2o_net_create / l2o_net_destroy    networks.factory + StandardDeepLSTM.__init__   DM/networks.py:34-44,157-205
  *   l2o_theta_count / l2o_theta_layout  snt.get_variables_in_module order              DM/networks.py:47-62
  *   l2o_state_floats                    Network.initial_state_for_inputs               DM/networks.py:234-236,273-276
+ *   l2o_workspace_bytes                 the loop-carried tensors + TensorArray of the while_loop  DM/meta.py:361-376
  *   l2o_step                            delta, state' = net(g, state)  (one time step) DM/networks.py:207-232,254-271,287-300
  *                                       + RNNProp Adam features                        DM/meta_rnnprop_train.py:383-388
  *                                       + x_next = x + delta                           DM/meta.py:352-353
@@ -126,6 +127,8 @@ typedef struct {
   const float* labels;  /* imitation mode: dDelta_t = (delta_t - label_t)/n_total */
   int64_t n_total;
   double* dtheta;       /* [P] += dL/dtheta */
+  const float* delta_seq; /* optional [T][n], imitation mode: the deltas l2o_unroll_fwd recorded for this unroll; lets the
+                             tensor-core BPTT form dDelta_t without recomputing the output layer (exact-fp32 engine ignores it) */
 } l2o_bwd_args;
 
 int l2o_net_create(l2o_handle* out, const l2o_net_desc* desc);
@@ -133,6 +136,11 @@ void l2o_net_destroy(l2o_handle h);
 int l2o_net_set_engine(l2o_handle h, int32_t engine);
 int64_t l2o_theta_count(l2o_handle h);
 int64_t l2o_state_floats(l2o_handle h); /* per coordinate: 2*sum(H_l) */
+/* Caller-owned buffer sizes (bytes) for n coordinates and an unroll of T steps (l2o_workspace_bytes).
+ * fwd_bytes: state arena + [T+1] checkpoint arenas + g_rec [T+1][n] + feat_rec [T][2][n] (n_in == 2 only);
+ * bwd_bytes: what l2o_unroll_bwd reads of those (ckpt + g_rec/in_seq) + the fp64 dtheta accumulator.
+ * The library itself allocates nothing per call (only a per-net weight image of < 100 KB at first tensor-core use). */
+int l2o_workspace_bytes(l2o_handle h, int64_t n, int32_t T, size_t* fwd_bytes, size_t* bwd_bytes);
 
 int l2o_step(l2o_handle h, const l2o_step_args* a, void* stream);
 int l2o_unroll_fwd(l2o_handle h, const l2o_unroll_args* a, void* stream);

@@ -23,7 +23,7 @@ ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
 
 # every symbol include/l2o_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "l2o_net_create", "l2o_net_destroy", "l2o_net_set_engine", "l2o_theta_count", "l2o_state_floats",
+    "l2o_net_create", "l2o_net_destroy", "l2o_net_set_engine", "l2o_theta_count", "l2o_state_floats", "l2o_workspace_bytes",
     "l2o_step", "l2o_unroll_fwd", "l2o_unroll_bwd", "l2o_adam_step", "l2o_log_and_sign",
     "l2o_launch_count", "l2o_status_string", "l2o_last_cuda_error", "l2o_version",
 ]
@@ -54,7 +54,7 @@ class UnrollArgs(C.Structure):
 
 class BwdArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("theta", _fp), ("in_seq", _fp), ("ckpt", _fp), ("g_rec", _fp),
-                ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp)]
+                ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp), ("delta_seq", _fp)]
 
 
 class L2OError(RuntimeError):
@@ -134,6 +134,8 @@ def lib():
     L.l2o_theta_count.restype = C.c_int64
     L.l2o_state_floats.argtypes = [C.c_void_p]
     L.l2o_state_floats.restype = C.c_int64
+    L.l2o_workspace_bytes.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.l2o_workspace_bytes.restype = C.c_int
     L.l2o_step.argtypes = [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]
     L.l2o_step.restype = C.c_int
     L.l2o_unroll_fwd.argtypes = [C.c_void_p, C.POINTER(UnrollArgs), C.c_void_p]

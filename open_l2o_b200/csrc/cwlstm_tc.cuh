@@ -140,6 +140,114 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float
                "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
                : "memory");
 }
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float a, float b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b))
+               : "memory");
+}
+// Asynchronous TMEM -> register load of N consecutive columns of this thread's lane (N = 2, 4, 8, 16).  The caller
+// issues tc_wait_ld() before reading v (several loads may be in flight behind one wait).
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, float* v) {
+  static_assert(N == 2 || N == 4 || N == 8 || N == 16, "unsupported TMEM load width");
+  uint32_t r[N];
+  if constexpr (N == 2) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+  } else if constexpr (N == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = __uint_as_float(r[k]);  // register renames only; values are valid after the wait
+}
+
+// ---- thread-pair work split -------------------------------------------------------------------------------------
+// A coordinate is served by a PAIR of epilogue threads (same TMEM lane, warps w and w+4).  Half 0 owns hidden units
+// [0, kSplit) of both layers, half 1 the rest plus the per-coordinate scalar work (optimizee / preprocessing / output
+// layer), which is worth about two units — hence 12 | 8 (measured: 10 | 10 is 4 % slower, it only adds x2 accesses).
+// Each half walks its units in chunks of 4 (or 2) units, so that every chunk is a naturally aligned group for the
+// 8/16-byte global and shared accesses and for the x2/x4 (one column per unit) and x8/x16 (four gate columns per
+// unit) TMEM accesses.  f(K0, NC): K0 = index of the chunk's first unit in the thread's arrays (unit = U0 + K0),
+// NC = units in the chunk; both are compile-time constants (IC<>).
+#ifndef L2O_SPLIT_UNITS
+#define L2O_SPLIT_UNITS 12
+#endif
+constexpr int kSplit = L2O_SPLIT_UNITS;
+static_assert(kSplit == 12 || kSplit == 10, "supported thread-pair splits: 12|8 and 10|10");
+template <int HALF>
+struct HalfUnits {
+  static constexpr int U0 = HALF == 0 ? 0 : kSplit;
+  static constexpr int NU = HALF == 0 ? kSplit : kH - kSplit;
+};
+template <int N>
+struct IC {
+  static constexpr int value = N;
+};
+template <int HALF, class F>
+__device__ __forceinline__ void for_chunks(F&& f) {
+  if constexpr (kSplit == 12) {
+    f(IC<0>{}, IC<4>{});
+    f(IC<4>{}, IC<4>{});
+    if constexpr (HALF == 0) f(IC<8>{}, IC<4>{});
+  } else if constexpr (HALF == 0) {
+    f(IC<0>{}, IC<4>{});
+    f(IC<4>{}, IC<4>{});
+    f(IC<8>{}, IC<2>{});
+  } else {
+    f(IC<0>{}, IC<2>{});
+    f(IC<2>{}, IC<4>{});
+    f(IC<6>{}, IC<4>{});
+  }
+}
+#define L2O_CHUNK(K0, NC, k0c, ncc)                 \
+  constexpr int K0 = decltype(k0c)::value;          \
+  constexpr int NC = decltype(ncc)::value
+// global <-> register copies of the thread's units (p already points at unit U0 of the coordinate's row)
+template <int HALF>
+__device__ __forceinline__ void load_units(const float* __restrict__ p, float* v) {
+  for_chunks<HALF>([&](auto k0c, auto ncc) {
+    L2O_CHUNK(K0, NC, k0c, ncc);
+    if constexpr (NC == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(p + K0);
+      v[K0] = t.x; v[K0 + 1] = t.y; v[K0 + 2] = t.z; v[K0 + 3] = t.w;
+    } else {
+      const float2 t = *reinterpret_cast<const float2*>(p + K0);
+      v[K0] = t.x; v[K0 + 1] = t.y;
+    }
+  });
+}
+template <int HALF>
+__device__ __forceinline__ void store_units(float* __restrict__ p, const float* v) {
+  for_chunks<HALF>([&](auto k0c, auto ncc) {
+    L2O_CHUNK(K0, NC, k0c, ncc);
+    if constexpr (NC == 4) *reinterpret_cast<float4*>(p + K0) = make_float4(v[K0], v[K0 + 1], v[K0 + 2], v[K0 + 3]);
+    else *reinterpret_cast<float2*>(p + K0) = make_float2(v[K0], v[K0 + 1]);
+  });
+}
+// per-unit TMEM columns [col0, col0+NU) of this lane -> v (one wait for the three loads)
+template <int HALF>
+__device__ __forceinline__ void tmem_ld_units(uint32_t taddr, float* v) {
+  for_chunks<HALF>([&](auto k0c, auto ncc) {
+    L2O_CHUNK(K0, NC, k0c, ncc);
+    tmem_ldn<NC>(taddr + K0, v + K0);
+  });
+  tc_wait_ld();
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -219,6 +327,7 @@ __device__ __forceinline__ float ext_weight_bwd(const float* __restrict__ theta,
 }
 
 // mode 0: forward image (B1 | B2, hi/lo);  mode 1: BPTT image (B1' | B2' in the BPTT operand order, then T1 | T2)
+constexpr float kLog2e = 1.4426950408889634f;
 template <class C>
 __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __restrict__ img, int with_transposed) {
   static_assert(C::H1 == kH && C::H2 == kH && C::F <= 3 && !C::FC, "tc engine: LSTM-20x2, F <= 3");
@@ -260,31 +369,22 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
 }
 
 // ------------------------------------------------------------------ epilogue helpers
-// One LSTM unit, pointwise.  Default form: 8 MUFU ops (5 ex2 + 3 rcp) instead of the 10 of five separate
-// sigmoid/tanh evaluations — sigma(i)*tanh(j) = (1-Ej) / ((1+Ei)(1+Ej)) and tanh(c')*sigma(o) likewise share one
-// reciprocal.  The exponents are clamped to 2^63 so the shared denominator stays finite (sigma/tanh are saturated to
-// fp32 precision long before that).  The activation pipe is the forward kernel's busiest unit (ncu: XU 50 %).
+// One LSTM unit, pointwise, from the four accumulator columns (pre-activations i, j, f, o) of the unit.  8 MUFU ops
+// (5 ex2 + 3 rcp) instead of the 10 of five separate sigmoid/tanh evaluations: sigma(i) tanh(j) =
+// (1-Ej) / ((1+Ei)(1+Ej)) and tanh(c') sigma(o) likewise share one reciprocal.  The exponents are clamped to 2^63
+// so the shared denominator stays finite (sigma/tanh are saturated to fp32 precision long before that).  The
+// activation pipe is the forward kernel's busiest unit (ncu: XU 50 %).  (Folding the -log2(e) factors into the
+// weight images was measured too: -0.7 % time, 1.5x the d-theta error — not kept.)
 __device__ __forceinline__ void lstm_point_fwd(float zi, float zj, float zf, float zo, float& c, float& h) {
-#ifdef L2O_FWD_MUFU10
-  const float i = sigmoid_fast(zi);
-  const float j = tanh_fast(zj);
-  const float f = sigmoid_fast(zf + 1.0f);
-  const float o = sigmoid_fast(zo);
-  const float cn = fmaf(f, c, i * j);
-  c = cn;
-  h = tanh_fast(cn) * o;
-#else
-  constexpr float kL = 1.4426950408889634f;
-  const float Ei = ex2_approx(fminf(-kL * zi, 63.f));
-  const float Ej = ex2_approx(fminf(-2.f * kL * zj, 63.f));
-  const float f = rcp_approx(1.0f + ex2_approx(fmaf(-kL, zf, -kL)));
+  const float Ei = ex2_approx(fminf(-kLog2e * zi, 63.f));
+  const float Ej = ex2_approx(fminf(-2.f * kLog2e * zj, 63.f));
+  const float f = rcp_approx(1.0f + ex2_approx(fmaf(-kLog2e, zf, -kLog2e)));
   const float ij = (1.0f - Ej) * rcp_approx((1.0f + Ei) * (1.0f + Ej));
   const float cn = fmaf(f, c, ij);
   c = cn;
-  const float Ec = ex2_approx(fminf(-2.f * kL * cn, 63.f));
-  const float Eo = ex2_approx(fminf(-kL * zo, 63.f));
+  const float Ec = ex2_approx(fminf(-2.f * kLog2e * cn, 63.f));
+  const float Eo = ex2_approx(fminf(-kLog2e * zo, 63.f));
   h = (1.0f - Ec) * rcp_approx((1.0f + Ec) * (1.0f + Eo));
-#endif
 }
 // LSTM pointwise update of 4 hidden units from 16 accumulator columns (i,j,f,o interleaved).
 __device__ __forceinline__ void lstm_units4(const float* z, float* c, float* h) {
@@ -301,6 +401,22 @@ __device__ __forceinline__ void st_split4(uint32_t a_hi, uint32_t a_lo, int col,
   split_tf32(v[3], h3, l3);
   tmem_st4(a_hi + col, h0, h1, h2, h3);
   tmem_st4(a_lo + col, l0, l1, l2, l3);
+}
+__device__ __forceinline__ void st_split2(uint32_t a_hi, uint32_t a_lo, int col, const float* v) {
+  float h0, h1, l0, l1;
+  split_tf32(v[0], h0, l0);
+  split_tf32(v[1], h1, l1);
+  tmem_st2(a_hi + col, h0, h1);
+  tmem_st2(a_lo + col, l0, l1);
+}
+// the thread's NU per-unit values -> A_hi / A_lo columns [col0, col0+NU)  (col0 = column of the thread's first unit)
+template <int HALF>
+__device__ __forceinline__ void st_split_units(uint32_t a_hi, uint32_t a_lo, int col0, const float* v) {
+  for_chunks<HALF>([&](auto k0c, auto ncc) {
+    L2O_CHUNK(K0, NC, k0c, ncc);
+    if constexpr (NC == 4) st_split4(a_hi, a_lo, col0 + K0, v + K0);
+    else st_split2(a_hi, a_lo, col0 + K0, v + K0);
+  });
 }
 
 __device__ __forceinline__ void lstm_unit_fwd(const float* z, float& c, float& h) {
@@ -323,8 +439,8 @@ struct Smem {
 template <class C, int HALF>
 __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const NetRt& rt, Smem& S, uint32_t tmem_base,
                                              float* __restrict__ state_out, int warp, int lane) {
-  constexpr int U0 = HALF == 0 ? 0 : 12;
-  constexpr int NU = HALF == 0 ? 12 : 8;
+  constexpr int U0 = HalfUnits<HALF>::U0;
+  constexpr int NU = HalfUnits<HALF>::NU;
   const int tile = warp >> 3;          // warps 0-7: tile 0, 8-15: tile 1
   const int q = warp & 3;              // TMEM lane quarter
   const int row = q * 32 + lane;       // coordinate within the tile
@@ -354,24 +470,21 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
 #pragma unroll
       for (int k = 0; k < NU; ++k) { h1[k] = 0.f; h2[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
       if (act) {
-        load_vec<NU>(a.state + i * kH + U0, h1);
-        load_vec<NU>(a.state + (n + i) * kH + U0, c1);
-        load_vec<NU>(a.state + 2 * n * kH + i * kH + U0, h2);
-        load_vec<NU>(a.state + 2 * n * kH + (n + i) * kH + U0, c2);
+        load_units<HALF>(a.state + i * kH + U0, h1);
+        load_units<HALF>(a.state + (n + i) * kH + U0, c1);
+        load_units<HALF>(a.state + 2 * n * kH + i * kH + U0, h2);
+        load_units<HALF>(a.state + 2 * n * kH + (n + i) * kH + U0, c2);
         if (a.ckpt) {
-          store_vec<NU>(a.ckpt + i * kH + U0, h1);
-          store_vec<NU>(a.ckpt + (n + i) * kH + U0, c1);
-          store_vec<NU>(a.ckpt + 2 * n * kH + i * kH + U0, h2);
-          store_vec<NU>(a.ckpt + 2 * n * kH + (n + i) * kH + U0, c2);
+          store_units<HALF>(a.ckpt + i * kH + U0, h1);
+          store_units<HALF>(a.ckpt + (n + i) * kH + U0, c1);
+          store_units<HALF>(a.ckpt + 2 * n * kH + i * kH + U0, h2);
+          store_units<HALF>(a.ckpt + 2 * n * kH + (n + i) * kH + U0, c2);
         }
         if (a.x) x = a.x[i];
         if (in_kernel_opt) { oa = a.opt_a[i]; ob = a.opt_b[i]; }
       }
-#pragma unroll
-      for (int g4 = 0; g4 < NU / 4; ++g4) {
-        st_split4(t_ah, t_al, kColH1 + U0 + 4 * g4, h1 + 4 * g4);
-        st_split4(t_ah, t_al, kColH2 + U0 + 4 * g4, h2 + 4 * g4);
-      }
+      st_split_units<HALF>(t_ah, t_al, kColH1 + U0, h1);
+      st_split_units<HALF>(t_ah, t_al, kColH2 + U0, h2);
     }
     for (int t = 0; t < T; ++t) {
       // ---- gradient + preprocessing -> feature chunk of A (half 1 owns the per-coordinate scalars) ----------
@@ -406,41 +519,47 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       pd ^= 1;
       tc_fence_after();
       float hrow[NU];
+      {
+        float z[4 * NU];  // this thread's 40 gate pre-activations: three loads in flight behind one wait
+        for_chunks<HALF>([&](auto k0c, auto ncc) {
+          L2O_CHUNK(K0, NC, k0c, ncc);
+          tmem_ldn<4 * NC>(t_d + 4 * (U0 + K0), z + 4 * K0);
+        });
+        tc_wait_ld();
 #pragma unroll
-      for (int g4 = 0; g4 < NU / 4; ++g4) {
-        float z[16];
-        tmem_ld16(t_d + 4 * U0 + 16 * g4, z);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) lstm_unit_fwd(z + 4 * u, c1[4 * g4 + u], hrow[4 * g4 + u]);
-        st_split4(t_ah, t_al, kColH1 + U0 + 4 * g4, hrow + 4 * g4);
+        for (int k = 0; k < NU; ++k) lstm_unit_fwd(z + 4 * k, c1[k], hrow[k]);
       }
+      st_split_units<HALF>(t_ah, t_al, kColH1 + U0, hrow);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready[tile]);
       if (act) {
         if (a.ckpt) {
           float* ck = a.ckpt + (int64_t)(t + 1) * slot;
-          store_vec<NU>(ck + i * kH + U0, hrow);
-          store_vec<NU>(ck + (n + i) * kH + U0, c1);
+          store_units<HALF>(ck + i * kH + U0, hrow);
+          store_units<HALF>(ck + (n + i) * kH + U0, c1);
         }
-        if (t == T - 1) store_vec<NU>(state_out + i * kH + U0, hrow);  // final hidden state of layer 1
+        if (t == T - 1) store_units<HALF>(state_out + i * kH + U0, hrow);  // final hidden state of layer 1
       }
       // ---- layer 2 epilogue + output linear + parameter add ---------------------------------
       mbar_wait(&S.d_ready[tile], pd);
       pd ^= 1;
       tc_fence_after();
       float yp = 0.f;
+      {
+        float z[4 * NU];
+        for_chunks<HALF>([&](auto k0c, auto ncc) {
+          L2O_CHUNK(K0, NC, k0c, ncc);
+          tmem_ldn<4 * NC>(t_d + 4 * (U0 + K0), z + 4 * K0);
+        });
+        tc_wait_ld();
 #pragma unroll
-      for (int g4 = 0; g4 < NU / 4; ++g4) {
-        float z[16];
-        tmem_ld16(t_d + 4 * U0 + 16 * g4, z);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          lstm_unit_fwd(z + 4 * u, c2[4 * g4 + u], hrow[4 * g4 + u]);
-          yp = fmaf(hrow[4 * g4 + u], S.wo[U0 + 4 * g4 + u], yp);
+        for (int k = 0; k < NU; ++k) {
+          lstm_unit_fwd(z + 4 * k, c2[k], hrow[k]);
+          yp = fmaf(hrow[k], S.wo[U0 + k], yp);
         }
-        st_split4(t_ah, t_al, kColH2 + U0 + 4 * g4, hrow + 4 * g4);
       }
+      st_split_units<HALF>(t_ah, t_al, kColH2 + U0, hrow);
       // exchange the output-layer partial sums inside the thread pair (named barrier: the tile's 256 threads)
       S.ypart[tile][HALF][row] = yp;
       asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
@@ -450,10 +569,10 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       if (act) {
         if (a.ckpt) {
           float* ck = a.ckpt + (int64_t)(t + 1) * slot + 2 * n * kH;
-          store_vec<NU>(ck + i * kH + U0, hrow);
-          store_vec<NU>(ck + (n + i) * kH + U0, c2);
+          store_units<HALF>(ck + i * kH + U0, hrow);
+          store_units<HALF>(ck + (n + i) * kH + U0, c2);
         }
-        if (t == T - 1) store_vec<NU>(state_out + 2 * n * kH + i * kH + U0, hrow);  // final hidden state of layer 2
+        if (t == T - 1) store_units<HALF>(state_out + 2 * n * kH + i * kH + U0, hrow);  // final hidden state of layer 2
         if (HALF == 1) {
           if (a.delta_seq) a.delta_seq[(int64_t)t * n + i] = d;
           if (a.labels) {
@@ -473,8 +592,8 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
           if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gT;
         }
         if (T > 0) {
-          store_vec<NU>(state_out + (n + i) * kH + U0, c1);
-          store_vec<NU>(state_out + 2 * n * kH + (n + i) * kH + U0, c2);
+          store_units<HALF>(state_out + (n + i) * kH + U0, c1);
+          store_units<HALF>(state_out + 2 * n * kH + (n + i) * kH + U0, c2);
         }
         if (HALF == 1 && a.x) a.x[i] = x;
       }

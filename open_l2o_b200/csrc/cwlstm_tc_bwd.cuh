@@ -173,7 +173,11 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
     float dh1c[NU], dc1c[NU], dh2c[NU], dc2c[NU];
 #pragma unroll
     for (int k = 0; k < NU; ++k) { dh1c[k] = 0.f; dc1c[k] = 0.f; dh2c[k] = 0.f; dc2c[k] = 0.f; }
-    float lam = act ? a.g_rec[(int64_t)T * n + i] : 0.f;
+    // dDelta_t: meta-loss mode = running suffix sum of the recorded gradients; imitation mode =
+    // (delta_t - label_t) / N_total from the forward pass's recorded deltas (DM/meta_dm_train.py:472-475)
+    const bool imit = a.labels != nullptr;
+    const float inv_nt = imit ? 1.0f / (float)a.n_total : 0.f;
+    float lam = (act && !imit) ? a.g_rec[(int64_t)T * n + i] : 0.f;
 
     for (int t = T - 1; t >= 0; --t) {
       const float* ck = a.ckpt + (int64_t)t * slot;
@@ -186,6 +190,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       for (int k = 0; k < NU; ++k) { h1p[k] = 0.f; h1n[k] = 0.f; h2p[k] = 0.f; c1p[k] = 0.f; c2p[k] = 0.f; }
       float raw0 = 0.f;
       if (HALF == 1 && act) raw0 = a.in_seq[(int64_t)t * n + i];  // only half 1 owns the feature chunk
+      if (imit && act) lam = (a.delta_seq[(int64_t)t * n + i] - a.labels[(int64_t)t * n + i]) * inv_nt;
       if (act) {
         load_vec<NU>(ck + i * kH + U0, h1p);
         load_vec<NU>(ck + slot + i * kH + U0, h1n);
@@ -200,7 +205,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
           asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
           if (HALF == 1) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_seq + (int64_t)(t - 1) * n + i));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.g_rec + (int64_t)(t - 1) * n + i));
+            if (!imit) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.g_rec + (int64_t)(t - 1) * n + i));
           }
         }
       }
@@ -334,7 +339,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
       mbar_arrive(&S.a_ready);
       dx1_pending = true;
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      if (act) lam += a.g_rec[(int64_t)t * n + i];
+      if (act && !imit) lam += a.g_rec[(int64_t)t * n + i];
     }
   }
   if (dx1_pending) {  // drain the last dX1 completion so the barrier phase bookkeeping stays consistent

@@ -110,6 +110,17 @@ int l2o_net_set_engine(l2o_handle h, int32_t engine) {
 int64_t l2o_theta_count(l2o_handle h) { return h ? h->n_theta : L2O_E_INVALID; }
 int64_t l2o_state_floats(l2o_handle h) { return h ? h->state_floats : L2O_E_INVALID; }
 
+int l2o_workspace_bytes(l2o_handle h, int64_t n, int32_t T, size_t* fwd_bytes, size_t* bwd_bytes) {
+  if (!h || n < 0 || T < 0) return L2O_E_INVALID;
+  const size_t arena = (size_t)h->state_floats * (size_t)n * sizeof(float);
+  const size_t ckpt = arena * ((size_t)T + 1);
+  const size_t grec = (size_t)(T + 1) * (size_t)n * sizeof(float);
+  const size_t feat = h->desc.n_in == 2 ? (size_t)T * 2 * (size_t)n * sizeof(float) : 0;
+  if (fwd_bytes) *fwd_bytes = arena + ckpt + grec + feat;
+  if (bwd_bytes) *bwd_bytes = ckpt + grec + feat + (size_t)h->n_theta * sizeof(double);
+  return L2O_OK;
+}
+
 int l2o_step(l2o_handle h, const l2o_step_args* a, void* stream) {
   if (!h || !a || a->n < 0 || !a->theta || !a->in0) return L2O_E_INVALID;
   if (h->state_floats > 0 && (!a->state_in || !a->state_out)) return L2O_E_INVALID;

@@ -23,7 +23,9 @@ static int ensure_image(l2o_net* h) {
 }
 
 bool tc_bwd_ok(const l2o_net* h, const l2o_bwd_args& a) {
-  return tc_supported(h->cfg) && a.g_rec != nullptr && a.labels == nullptr && !h->rt.tanh_output;
+  // meta-loss mode (lambda suffix sums of g_rec) or imitation mode with the forward pass's recorded deltas
+  const bool mode_ok = a.labels ? (a.delta_seq != nullptr && a.n_total > 0) : a.g_rec != nullptr;
+  return tc_supported(h->cfg) && mode_ok && !h->rt.tanh_output;
 }
 
 int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {

@@ -71,6 +71,12 @@ class NetHandle:
         except Exception:
             pass
 
+    def workspace_bytes(self, n: int, T: int):
+        """(forward, backward) caller-owned buffer bytes for n coordinates and a T-step unroll."""
+        f, b = C.c_size_t(), C.c_size_t()
+        _lib.check(_lib.lib().l2o_workspace_bytes(self._h, n, T, C.byref(f), C.byref(b)), "l2o_workspace_bytes")
+        return int(f.value), int(b.value)
+
     def set_engine(self, engine: int):
         _lib.check(_lib.lib().l2o_net_set_engine(self._h, engine), "l2o_net_set_engine")
 
@@ -125,7 +131,7 @@ class NetHandle:
         a.n_total = n_total
         _lib.check(_lib.lib().l2o_unroll_fwd(self._h, C.byref(a), _stream()), "l2o_unroll_fwd")
 
-    def unroll_bwd(self, theta, n, T, in_seq, ckpt, dtheta, *, g_rec=None, labels=None, n_total=0):
+    def unroll_bwd(self, theta, n, T, in_seq, ckpt, dtheta, *, g_rec=None, labels=None, n_total=0, delta_seq=None):
         a = BwdArgs()
         a.n, a.T = n, T
         a.theta = _ptr(theta, name="theta")
@@ -133,6 +139,7 @@ class NetHandle:
         a.g_rec, a.labels = _ptr(g_rec, name="g_rec"), _ptr(labels, name="labels")
         a.n_total = n_total
         a.dtheta = _ptr(dtheta, torch.float64, "dtheta")
+        a.delta_seq = _ptr(delta_seq, name="delta_seq")
         _lib.check(_lib.lib().l2o_unroll_bwd(self._h, C.byref(a), _stream()), "l2o_unroll_bwd")
 
 

@@ -491,6 +491,7 @@ class _MtTask(object):
             sf = h.state_floats
             self.subsets.append(dict(run=r, n=r.n, state=h.new_state(r.n, prog.device),
                                      ckpt=torch.zeros((T + 1) * max(sf * r.n, 1), device=prog.device),
+                                     dseq=torch.zeros(T * r.n, device=prog.device),
                                      inp=Placeholder("mt{}_input_subset{}".format(index, len(self.subsets))),
                                      lab=Placeholder("mt{}_label_subset{}".format(index, len(self.subsets)))))
         self.n_total = sum(sb["n"] for sb in self.subsets)
@@ -520,9 +521,10 @@ class _MtTask(object):
             inp, lab = self._dev(feed[sb["inp"]], T, n), self._dev(feed[sb["lab"]], T, n)
             work = sb["state"].clone()
             h.unroll_fwd(r.net.theta, n, T, work, in_seq=inp, ckpt=sb["ckpt"] if train else None, labels=lab,
-                         imit_loss=self.il, n_total=self.n_total)
-            if train:
-                h.unroll_bwd(r.net.theta, n, T, inp, sb["ckpt"], prog.dtheta[r.key], labels=lab, n_total=self.n_total)
+                         imit_loss=self.il, n_total=self.n_total, delta_seq=sb["dseq"] if train else None)
+            if train:  # the recorded deltas let the tensor-core BPTT run in imitation mode too
+                h.unroll_bwd(r.net.theta, n, T, inp, sb["ckpt"], prog.dtheta[r.key], labels=lab, n_total=self.n_total,
+                             delta_seq=sb["dseq"])
             finals.append(work)
         out = {}
         if "loss_mt" in kinds:

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for v in "" _MUFU10 _TRUNC _NOMASK; do
+for v in ""; do
   export L2O_LIB=/root/repo/open_l2o_b200/csrc/libl2o_b200$v.so
   echo "=== $L2O_LIB"
   timeout 300 python scripts/tc_accuracy.py 2>&1 | tail -6
@@ -11,4 +11,5 @@ for l in sys.stdin:
 "
 done
 unset L2O_LIB
-timeout 600 python -m pytest tests/test_tc_gpu.py -x -q 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_tc_gpu.py tests/test_meta_gpu.py -x -q 2>&1 | tail -3
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 3000 gpurun_out/bench_default.json; tail -5 gpurun_out/bench_default.err

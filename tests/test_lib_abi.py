@@ -42,6 +42,10 @@ def test_net_create_validates_without_gpu():
     assert NetHandle(layers=(20, 20), preprocess_name="fc", preprocess_options={"dim": 20}, n_in=2).n_theta == 6641
     with pytest.raises(_lib.L2OError):
         NetHandle(layers=(33, 5))
+    # caller-owned buffers of BASELINE config #5 on one GPU: 1M coordinates x T=100 (32.3 GB of checkpoints)
+    fwd, bwd = h.workspace_bytes(1_000_000, 100)
+    assert fwd == 4 * (80 * 1_000_000 * 102 + 101 * 1_000_000)
+    assert bwd == 4 * (80 * 1_000_000 * 101 + 101 * 1_000_000) + 8 * 5061
 
 
 def test_product_package_never_imports_oracle():

@@ -145,3 +145,40 @@ def test_tc_step_operator(name):
         for (hg, cg), (hr, cr) in zip(arena_to_state(a_out.cpu(), spec.layers, n), st):
             assert rel_err(hg, hr) <= REL_TOL and rel_err(cg, cr) <= REL_TOL
         a_in = a_out
+
+
+@pytest.mark.parametrize("name", ["dm_identity", "dm_logsign"])
+def test_tc_imitation_bptt(name):
+    """Imitation ("mt") unroll on the tcgen05 engine (DM/meta_dm_train.py:463-480): forward over pre-recorded inputs
+    records delta_seq; the tensor-core BPTT forms dDelta_t = (delta_t - label_t)/N from it."""
+    from open_l2o_b200.engine import ENGINE_TC
+    spec = SPECS[name]
+    n, T = 148 * 128 + 19, 7
+    gen = torch.Generator().manual_seed(13)
+    theta = _theta(spec, gain=1.0)
+    inputs = torch.randn(T, n, generator=gen)
+    labels = torch.randn(T, n, generator=gen) * 0.01
+    th64 = theta.double().requires_grad_(True)
+    loss64, _, _ = orc.imitation_loss(spec, th64, inputs.double(), labels.double(),
+                                      orc.initial_state(spec, n, torch.float64))
+    (g64,) = torch.autograd.grad(loss64, th64)
+    th32 = theta.clone().requires_grad_(True)
+    loss32, _, _ = orc.imitation_loss(spec, th32, inputs, labels, orc.initial_state(spec, n))
+    (g32,) = torch.autograd.grad(loss32, th32)
+    h = make_handle(spec)
+    h.set_engine(ENGINE_TC)   # explicit engine: an unsupported mode would raise instead of falling back
+    sf = h.state_floats
+    th, seq, lab = theta.to(DEV), inputs.contiguous().to(DEV), labels.to(DEV)
+    arena = h.new_state(n, DEV)
+    ckpt = torch.zeros((T + 1) * sf * n, device=DEV)
+    dseq = torch.zeros(T * n, device=DEV)
+    il = torch.zeros(1, dtype=torch.float64, device=DEV)
+    h.unroll_fwd(th, n, T, arena, in_seq=seq, ckpt=ckpt, labels=lab, imit_loss=il, n_total=n, delta_seq=dseq)
+    assert rel_err(il, loss64) <= REL_TOL
+    dtheta = torch.zeros(h.n_theta, dtype=torch.float64, device=DEV)
+    h.unroll_bwd(th, n, T, seq, ckpt, dtheta, labels=lab, n_total=n, delta_seq=dseq)
+    torch.cuda.synchronize()
+    slack = max(REL_TOL, 3.0 * rel_err(g32, g64))
+    assert rel_err(dtheta, g64) <= slack, (rel_err(dtheta, g64), rel_err(g32, g64))
+    with pytest.raises(Exception):   # imitation mode without the recorded deltas is not a tensor-core mode
+        h.unroll_bwd(th, n, T, seq, ckpt, dtheta, labels=lab, n_total=n)
