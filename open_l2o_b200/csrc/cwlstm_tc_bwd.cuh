@@ -18,7 +18,10 @@ using namespace tc;
 
 constexpr int kEpi = 256;
 constexpr int kThreadsB = kEpi + 128;
-constexpr int kEpiRegs = 224, kIssuerRegs = 40;
+#ifndef L2O_EPI_REGS
+#define L2O_EPI_REGS 224
+#endif
+constexpr int kEpiRegs = L2O_EPI_REGS, kIssuerRegs = 40;
 // TMEM column map.  The A operand of the gate recompute is ALIASED into the dZ operand region: it is dead once Z1/Z2
 // have completed (before dZ2 is written) and is rewritten only after the previous step's dX1 MMAs have drained.
 constexpr int cD1 = 0;                   // Z1 accumulators (read by the layer-1 backward phase)
@@ -27,7 +30,11 @@ constexpr int cAZh = 160, cAZl = 240;    // dZ rows (80 gate columns), hi / lo
 constexpr int cAh = cAZh, cAl = cAZl;    // A rows [h1p | u,1 | h1n | h2p] (64 columns), hi / lo -- aliased
 constexpr int cW2 = 320;                 // dW2^T accumulator: lanes = gate rows, 48 feature columns
 constexpr int cW1 = 368;                 // dW1^T accumulator: 32 feature columns
-static_assert(cW1 + 32 <= kTmemCols, "TMEM budget");
+// The layer-1 input rows [h1p | u,1] get their own (non-aliased) copy: the issuer runs Z2 first and commits it alone,
+// so the epilogue starts the layer-2 backward (which overwrites the aliased region with dZ2) while the Z1 MMAs are
+// still reading A1; Z1 is needed only by the layer-1 phase and is covered by the dX2 commit.
+constexpr int cA1h = 400, cA1l = 424;    // 24 columns each
+static_assert(cA1l + 24 <= kTmemCols, "TMEM budget");
 // Staged operand Y = [X (48 feature slots) | dZ (80 gate slots)] per coordinate, MN-major SWIZZLE_128B_BASE32B
 // (the only shared-memory layout the tensor core accepts for MN-major tf32; address map verified on the B200 with
 // scripts/umma_probe.cu):  byte(mn, c) = (c/4)*kYSBO + (mn/32)*kYLBO + (c%4)*128 + (((mn%32)/8) ^ (c%4))*32 + (mn%8)*4
@@ -148,6 +155,7 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
   const int c = q * 32 + lane;  // coordinate within the tile == TMEM lane
   const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t tD1 = tl + cD1, tD2 = tl + cD2, tAh = tl + cAh, tAl = tl + cAl, tAZh = tl + cAZh, tAZl = tl + cAZl;
+  const uint32_t tA1h = tl + cA1h, tA1l = tl + cA1l;
   const int T = a.T;
   const int64_t n = a.n;
   const int64_t slot = n * C::SF;
@@ -233,10 +241,15 @@ __device__ __forceinline__ void epilogue(const l2o_bwd_args& a, const NetRt& rt,
         }
       }
       if (prof) { L2O_PROF(HALF, pi); ++pi; }
-      if (HALF == 1) put4(tAh, tAl, kBColXC, u4, nullptr, nullptr, 0, true, false);
+      if (HALF == 1) {  // the feature chunk feeds both layers' bias row: aliased copy (Z2) + A1 copy (Z1)
+        put4(tAh, tAl, kBColXC, u4, nullptr, nullptr, 0, true, false);
+        put4(tA1h, tA1l, kBColXC, u4, nullptr, nullptr, 0, true, false);
+      }
 #pragma unroll
       for (int g4 = 0; g4 < NU / 4; ++g4) {
-        put4(tAh, tAl, U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
+        put4(tA1h, tA1l, U0 + 4 * g4, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
+        // aliased columns 16..19 sit inside Z2's contraction range (zero weight rows): keep them finite
+        if (U0 + 4 * g4 == kBZ2Start) put4(tAh, tAl, kBZ2Start, h1p + 4 * g4, nullptr, nullptr, 0, true, false);
         put4(tAh, tAl, kBColH1N + U0 + 4 * g4, h1n + 4 * g4, nullptr, nullptr, 0, true, false);
         put4(tAh, tAl, kBColH2P + U0 + 4 * g4, h2p + 4 * g4, nullptr, nullptr, 0, true, false);
       }
@@ -463,21 +476,17 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
       constexpr uint64_t kYStep = (2 * kYSBO) >> 4;       // 8 coordinates = two K atoms
       const uint32_t tD1 = tmem_base + cD1, tD2 = tmem_base + cD2, tAh = tmem_base + cAh, tAl = tmem_base + cAl;
       const uint32_t tAZh = tmem_base + cAZh, tAZl = tmem_base + cAZl, tW2 = tmem_base + cW2, tW1 = tmem_base + cW1;
+      const uint32_t tA1h = tmem_base + cA1h, tA1l = tmem_base + cA1l;
       uint32_t pa = 0;
       int pi = 0;
       (void)pi;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int t = T - 1; t >= 0; --t) {
-          // Z1 = A[0:24].B1'  and  Z2 = A[16:64].B2'  back to back (both depend only on checkpointed rows)
+          // Z2 = A[16:64].B2' first, committed alone (the layer-2 phase starts on it); then Z1 = A1[0:24].B1', which
+          // only the layer-1 phase reads, after the dX2 commit.  Both depend only on checkpointed rows.
           mbar_wait(&S.a_ready, pa); pa ^= 1; tc_fence_after();
           L2O_PROF(2, pi); ++pi;
           if (elect_one()) {
-#pragma unroll
-            for (int kc = 0; kc < kK1 / 8; ++kc) {
-              mma_tf32_ts(tD1, tAl + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
-              mma_tf32_ts(tD1, tAh + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
-              mma_tf32_ts(tD1, tAh + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
-            }
 #pragma unroll
             for (int kc = 0; kc < kK2 / 8; ++kc) {
               mma_tf32_ts(tD2, tAl + kBZ2Start + 8 * kc, b2h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
@@ -485,6 +494,12 @@ __global__ void __launch_bounds__(kThreadsB, 1) unroll_bwd_kernel(l2o_bwd_args a
               mma_tf32_ts(tD2, tAh + kBZ2Start + 8 * kc, b2h + kc * kFwdStep, id_fwd, 1u);
             }
             tc_commit(&S.d_ready);
+#pragma unroll
+            for (int kc = 0; kc < kK1 / 8; ++kc) {
+              mma_tf32_ts(tD1, tA1l + 8 * kc, b1h + kc * kFwdStep, id_fwd, kc > 0 ? 1u : 0u);
+              mma_tf32_ts(tD1, tA1h + 8 * kc, b1l + kc * kFwdStep, id_fwd, 1u);
+              mma_tf32_ts(tD1, tA1h + 8 * kc, b1h + kc * kFwdStep, id_fwd, 1u);
+            }
           }
           __syncwarp();
           L2O_PROF(2, pi); ++pi;
