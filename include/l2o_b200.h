@@ -153,6 +153,46 @@ int l2o_adam_step(float* theta, const double* dtheta, float* m, float* v, int64_
 /* out [2][n]: row 0 = max(log(|g|+eps)/k, -1), row 1 = clip(g*e^k, -1, 1). */
 int l2o_log_and_sign(const float* g, float* out, int64_t n, float k, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * L2O-Scale HierarchicalRNN update step (BASELINE config #4).
+ * SC/ = Model_Free_L2O/L2O-Scale/L2O-Scale-Training/ ; HR = SC/optimizer/hierarchical_rnn.py.
+ *
+ *   l2o_hrnn_create            HierarchicalRNN.__init__ + _create_slots (one slot set per optimizee tensor)   HR:69-218
+ *   l2o_hrnn_init_state        _initialize_state / _initialize_global_state                                    HR:303-350
+ *   l2o_hrnn_prepare           (derived quantities of a fresh / restored state: mean log-lr HR:432-442, first-step
+ *                               predicate SC/optimizer/utils.py:128-130, per-tensor gate bias HR:561-575)
+ *   l2o_hrnn_step              _compute_updates: one optimizer step over all tensors                          HR:353-430
+ *
+ * The flag set is the one the reference's drivers run (SC/metarun.py:154-225,243): levels [10,20,20], 4 gradient
+ * scales, grad products, log mean-squares, relative lr against the problem-wide mean, gradient shortcut, dynamic
+ * output scale, learnable decays / RNN init; no attention.  theta: flat fp32 [l2o_hrnn_theta_count()] in TF variable
+ * creation order (documented in open_l2o_b200/hierarchical_rnn.py THETA_SPEC).  state: 21 fp32 planes of [N]
+ * (N = sum of tensor sizes, tensors contiguous): 0-9 parameter (hidden), 10 scl_decay, 11 inp_decay,
+ * 12 log_learning_rate, 13-16 grad_accum1..4, 17-20 ms1..4.  layer: [n_tensors][20]; global: [20].
+ * workspace: caller-owned device buffer of l2o_hrnn_workspace_bytes() bytes, 256-byte aligned; it carries the
+ * per-tensor reductions from one step to the next, so it belongs to the state (call l2o_hrnn_prepare after writing
+ * the state from outside). */
+typedef struct l2o_hrnn* l2o_hrnn_handle;
+typedef struct {
+  const float* theta;
+  float* x;         /* [N] optimizee parameters, updated in place (not needed by init_state / prepare) */
+  const float* g;   /* [N] gradients */
+  float* state;     /* [21][N] */
+  float* layer;     /* [n_tensors][20] per-tensor RNN states */
+  float* global;    /* [20] global RNN state */
+  void* workspace;
+  float* update;    /* optional [N]: the applied step (x_old - x_new) */
+} l2o_hrnn_args;
+int l2o_hrnn_create(l2o_hrnn_handle* out, const int64_t* tensor_sizes, int32_t n_tensors);
+void l2o_hrnn_destroy(l2o_hrnn_handle h);
+int64_t l2o_hrnn_theta_count(void);
+int64_t l2o_hrnn_state_floats(void);           /* 21 per coordinate */
+int64_t l2o_hrnn_coords(l2o_hrnn_handle h);    /* N */
+int64_t l2o_hrnn_workspace_bytes(l2o_hrnn_handle h);
+int l2o_hrnn_init_state(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream); /* all planes but log_learning_rate */
+int l2o_hrnn_prepare(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream);
+int l2o_hrnn_step(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream);
+
 /* Number of this library's kernels launched so far in this process (bench.py's gpu_launches). */
 int64_t l2o_launch_count(void);
 const char* l2o_status_string(int status);

@@ -26,6 +26,8 @@ EXPORTS = [
     "l2o_net_create", "l2o_net_destroy", "l2o_net_set_engine", "l2o_theta_count", "l2o_state_floats", "l2o_workspace_bytes",
     "l2o_step", "l2o_unroll_fwd", "l2o_unroll_bwd", "l2o_adam_step", "l2o_log_and_sign",
     "l2o_launch_count", "l2o_status_string", "l2o_last_cuda_error", "l2o_version",
+    "l2o_hrnn_create", "l2o_hrnn_destroy", "l2o_hrnn_theta_count", "l2o_hrnn_state_floats", "l2o_hrnn_coords",
+    "l2o_hrnn_workspace_bytes", "l2o_hrnn_init_state", "l2o_hrnn_prepare", "l2o_hrnn_step",
 ]
 
 
@@ -55,6 +57,11 @@ class UnrollArgs(C.Structure):
 class BwdArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("theta", _fp), ("in_seq", _fp), ("ckpt", _fp), ("g_rec", _fp),
                 ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp), ("delta_seq", _fp)]
+
+
+class HrnnArgs(C.Structure):
+    _fields_ = [("theta", _fp), ("x", _fp), ("g", _fp), ("state", _fp), ("layer", _fp), ("global_", _fp),
+                ("workspace", _fp), ("update", _fp)]
 
 
 class L2OError(RuntimeError):
@@ -149,6 +156,20 @@ def lib():
     L.l2o_log_and_sign.restype = C.c_int
     L.l2o_launch_count.argtypes = []
     L.l2o_launch_count.restype = C.c_int64
+    L.l2o_hrnn_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32]
+    L.l2o_hrnn_create.restype = C.c_int
+    L.l2o_hrnn_destroy.argtypes = [C.c_void_p]
+    L.l2o_hrnn_destroy.restype = None
+    L.l2o_hrnn_theta_count.argtypes = []
+    L.l2o_hrnn_theta_count.restype = C.c_int64
+    L.l2o_hrnn_state_floats.argtypes = []
+    L.l2o_hrnn_state_floats.restype = C.c_int64
+    for name in ("l2o_hrnn_coords", "l2o_hrnn_workspace_bytes"):
+        getattr(L, name).argtypes = [C.c_void_p]
+        getattr(L, name).restype = C.c_int64
+    for name in ("l2o_hrnn_init_state", "l2o_hrnn_prepare", "l2o_hrnn_step"):
+        getattr(L, name).argtypes = [C.c_void_p, C.POINTER(HrnnArgs), C.c_void_p]
+        getattr(L, name).restype = C.c_int
     for name in ("l2o_status_string", "l2o_last_cuda_error", "l2o_version"):
         getattr(L, name).restype = C.c_char_p
     L.l2o_status_string.argtypes = [C.c_int]
