@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rastrigin", choices=["rastrigin", "lasso", "mlp", "rnnprop_mlp", "quadratic"])
+    ap.add_argument("--workload", default="rastrigin",
+                    choices=["rastrigin", "lasso", "mlp", "rnnprop_mlp", "quadratic", "hrnn_convnet"])
     ap.add_argument("--coords", type=int, default=0, help="coordinates per GPU (0 = workload default)")
     ap.add_argument("--unroll", type=int, default=0, help="T (0 = workload default)")
     ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tc"])
@@ -170,6 +171,89 @@ def quick_measure(workload, steps, warmup):
     return out
 
 
+def quick_measure_hrnn(steps, warmup, T=20, batch=128):
+    """BASELINE config #4: L2O-Scale HierarchicalRNN [10,20,20] optimizing a ConvNet on CIFAR-shaped synthetic data
+    (354,218 coordinates, unroll 20; inference path = the update step).  Also times the
+    step's three kernels alone on a large synthetic state for the HBM roofline of the per-coordinate kernel."""
+    from open_l2o_b200 import engine as eng, hierarchical_rnn as hr
+    from open_l2o_b200.scale_problems import ConvNet
+    dev = torch.device("cuda", torch.cuda.current_device())
+    prob = ConvNet((3, 32, 32), 10, [(3, 3, 32), (5, 5, 32)])
+    params = prob.init_tensors(seed=1, device=dev)
+    gen = torch.Generator().manual_seed(2)
+    data = torch.rand(batch, 32, 32, 3, generator=gen).to(dev)
+    labels = torch.nn.functional.one_hot(torch.randint(10, (batch,), generator=gen), 10).float().to(dev)
+    opt = hr.HierarchicalRNN(random_seed=0, **hr.metarun_flags())
+
+    def unroll():
+        for _ in range(T):
+            loss = prob.objective(params, data, labels)
+            grads = torch.autograd.grad(loss, params)
+            opt.apply_gradients(zip(grads, params))
+        return loss
+    for _ in range(warmup):
+        unroll()
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = unroll()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 1e3
+    n = opt.N
+    launches = int(eng.launch_count() - l0)
+    # the optimizer step alone (3 launches), same state
+    e0.record()
+    for _ in range(steps * T):
+        opt.step_flat()
+    e1.record()
+    torch.cuda.synchronize()
+    t_step = e0.elapsed_time(e1) / 1e3 / (steps * T)
+    out = {"workload": "L2O-Scale HierarchicalRNN [10,20,20], ConvNet 3x32x32 [(3,3,32),(5,5,32)] synthetic batch %d, "
+                       "unroll=%d (BASELINE config #4)" % (batch, T),
+           "coords": n, "unroll": T, "mode": "infer (optimizer step; meta-training of the HierarchicalRNN not built)",
+           "regime": "external-gradient (torch autograd ConvNet forward/backward between l2o_hrnn_step calls, eager)",
+           "value": n * T * steps / t, "unit": "coordinate-updates/s", "ms_per_step": 1e3 * t / steps, "steps": steps,
+           "warmup": warmup, "gpu_launches": launches, "last_fx": float(loss),
+           "optimizer_step_us": 1e6 * t_step}
+    del opt, params
+    # HBM roofline of the step on a state that does not fit L2: 16 tensors x 2M coordinates
+    sizes = [2_000_000] * 16
+    big = [torch.zeros(sz, device=dev).requires_grad_(True) for sz in sizes]
+    opt2 = hr.HierarchicalRNN(random_seed=0, **hr.metarun_flags())
+    g = [torch.randn(sz, device=dev) * 0.1 for sz in sizes]
+    opt2.apply_gradients(zip(g, big))
+    for _ in range(3):
+        opt2.step_flat()
+    torch.cuda.synchronize()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        opt2.step_flat()
+    e1.record()
+    torch.cuda.synchronize()
+    t_big = e0.elapsed_time(e1) / 1e3 / reps
+    nbig = opt2.N
+    bytes_per = 192.0   # coord kernel 88 B read + 88 B written, apply kernel 16 B (DESIGN.md 3.4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6500.0))
+    ach = bytes_per * nbig / t_big / 1e9
+    out["roofline"] = {"bound": "hbm", "kernel": "l2o::hrnn::coord_kernel + apply_kernel (one l2o_hrnn_step)",
+                       "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                       "coords": nbig, "ms": 1e3 * t_big, "coord_updates_per_s": nbig / t_big,
+                       "algorithmic_bytes_per_coord_update": bytes_per,
+                       "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s"}
+    del opt2, big, g
+    torch.cuda.empty_cache()
+    return out
+
+
 def pick_cpu_threads():
     """All host cores the op-for-op CPU path can actually use: intra-op threading of [N,80]-sized tensors stops
     scaling (and then regresses) beyond a few dozen threads, so cap at 32 and report the number used."""
@@ -227,6 +311,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "hrnn_convnet":   # side workload: its own line (N=1 only)
+        torch.cuda.set_device(0)
+        print(json.dumps(quick_measure_hrnn(steps=args.steps, warmup=args.warmup)))
+        return
 
     import torch.distributed as dist
     from open_l2o_b200 import engine as eng, meta
@@ -414,6 +502,10 @@ def main():
                 also.append(quick_measure(w, steps=max(args.steps, 5), warmup=max(args.warmup, 3)))
             except Exception as ex:  # the headline line must survive a failure of a side measurement
                 also.append({"workload": WORKLOADS[w][0], "error": repr(ex)[:200]})
+        try:
+            also.append(quick_measure_hrnn(steps=max(args.steps, 5), warmup=max(args.warmup, 3)))
+        except Exception as ex:
+            also.append({"workload": "L2O-Scale HierarchicalRNN (BASELINE config #4)", "error": repr(ex)[:200]})
 
     if rank == 0:
         line = {

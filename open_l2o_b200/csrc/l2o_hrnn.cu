@@ -68,7 +68,27 @@ inline size_t carve(Workspace& w, void* base, int nt, int64_t n) {
   return off;
 }
 
+// Per-coordinate transcendental work (34 sigmoid/tanh, 8 log, 11 sqrt, 4 divisions per coordinate-step) would cost
+// ~900 instructions in libdevice precision and make the step instruction-bound; the MUFU forms below (ex2 / lg2 /
+// rsq / rcp .approx, ~1e-7 relative) cut that to ~200.  The tiny upper-level kernel keeps libdevice math.
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float log_fast(float x) { return 0.6931471805599453f * lg2_approx(x); }
+__device__ __forceinline__ float exp_fast(float x) { return ex2_approx(1.4426950408889634f * x); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // per-parameter level (HR:444-540 features, rnn_cells.py:46-68 GRU, HR:606-706 readouts)
@@ -110,7 +130,7 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
     float dec[NS];
     dec[0] = d0;
 #pragma unroll
-    for (int s = 1; s < NS; ++s) dec[s] = sqrtf(dec[s - 1]);  // each accumulator on twice the timescale (HR:466-470)
+    for (int s = 1; s < NS; ++s) dec[s] = sqrt_approx(dec[s - 1]);  // each accumulator on twice the timescale (HR:466-470)
     float sc[NS], lm[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -119,9 +139,9 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
       const float acc = gi * (1.0f - dec[s]) + acc_old * dec[s];                 // HR:483-484
       const float dk = w.zero_flag[be.tensor * NS + s] ? 0.f : sd;               // utils.py:128-130
       const float ms = (1.0f - dk) * (acc * acc + 1e-12f) + dk * ms_old;         // utils.py:133-134
-      const float r = acc / sqrtf(ms + 1e-16f);
-      sc[s] = logf(r + sqrtf(1.0f + r * r));                                     // utils.asinh as written (utils.py:36-38)
-      lm[s] = logf(ms + 1e-16f);
+      const float r = acc * rsqrt_approx(ms + 1e-16f);
+      sc[s] = log_fast(r + sqrt_approx(fmaf(r, r, 1.0f)));                       // utils.asinh as written (utils.py:36-38)
+      lm[s] = log_fast(ms + 1e-16f);
       state[(int64_t)(P_ACC + s) * n + i] = acc;
       state[(int64_t)(P_MS + s) * n + i] = ms;
       if (ms != 0.f) nz_mask |= 1 << s;
@@ -156,8 +176,8 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
     float r[H0], u[H0];
 #pragma unroll
     for (int k = 0; k < H0; ++k) {
-      r[k] = sigmoidf_((pg[k] + sBg[k]) + sB0[k]);
-      u[k] = sigmoidf_((pg[H0 + k] + sBg[H0 + k]) + sB0[H0 + k]);
+      r[k] = sigmoid_fast((pg[k] + sBg[k]) + sB0[k]);
+      u[k] = sigmoid_fast((pg[H0 + k] + sBg[H0 + k]) + sB0[H0 + k]);
     }
 #pragma unroll
     for (int k = 0; k < H0; ++k) in[F + k] = r[k] * h[k];
@@ -178,7 +198,7 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
     float delta = 0.f, zs = 0.f, zi = 0.f, zl = 0.f;
 #pragma unroll
     for (int k = 0; k < H0; ++k) {
-      const float c = tanhf((pc[k] + sBc[k]) + sB0[2 * H0 + k]);
+      const float c = tanh_fast((pc[k] + sBc[k]) + sB0[2 * H0 + k]);
       hn[k] = u[k] * h[k] + (1.0f - u[k]) * c;
       state[(int64_t)(P_H + k) * n + i] = hn[k];
       delta = fmaf(hn[k], __ldg(theta + O_WU + k), delta);       // update direction (HR:609-611)
@@ -190,12 +210,12 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
 #pragma unroll
     for (int s = 0; s < NS; ++s) short_cut = fmaf(sc[s], __ldg(theta + O_G2D + s), short_cut);
     delta += short_cut;
-    const float scl_new = sigmoidf_(zs + __ldg(theta + O_BS));    // HR:645-651
-    const float inp_new = sigmoidf_(zi + __ldg(theta + O_BI));
+    const float scl_new = sigmoid_fast(zs + __ldg(theta + O_BS));    // HR:645-651
+    const float inp_new = sigmoid_fast(zi + __ldg(theta + O_BI));
     const float step_llr = fminf(fmaxf(llr + (zl + __ldg(theta + O_BL)), -33.0f), 33.0f);   // HR:667-683
-    const float lrm = sigmoidf_(__ldg(theta + O_LRM));
+    const float lrm = sigmoid_fast(__ldg(theta + O_LRM));
     const float llr_new = lrm * llr + (1.0f - lrm) * step_llr;    // HR:688-689
-    const float lr_param = expf(step_llr + __ldg(theta + O_OFF)); // HR:692
+    const float lr_param = exp_fast(step_llr + __ldg(theta + O_OFF)); // HR:692
     state[(int64_t)P_SCL * n + i] = scl_new;
     state[(int64_t)P_INP * n + i] = inp_new;
     state[(int64_t)P_LLR * n + i] = llr_new;
@@ -211,11 +231,11 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
   // block reduction of the 24 per-tensor sums (fp64) + the any(ms != 0) flags
   const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
-  for (int k = 0; k < kAcc; ++k) {
-    double v = (double)vals[k];
+  for (int k = 0; k < kAcc; ++k) {   // fp32 butterfly inside the warp (32 terms), fp64 across warps / blocks
+    float v = vals[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sRed[wid][k] = v;
+    if (lane == 0) sRed[wid][k] = (double)v;
   }
   const unsigned any0 = __ballot_sync(0xffffffffu, nz_mask & 1), any1 = __ballot_sync(0xffffffffu, nz_mask & 2);
   const unsigned any2 = __ballot_sync(0xffffffffu, nz_mask & 4), any3 = __ballot_sync(0xffffffffu, nz_mask & 8);
