@@ -15,3 +15,12 @@ opt.apply_gradients(zip([torch.randn(sz, device=dev) * 0.1 for sz in sizes], big
 for _ in range(3):
     opt.step_flat()
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    opt.step_flat()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print("hrnn step: %.3f ms for %d coords -> %.1f GB/s algorithmic (192 B/coord-step)" % (ms, opt.N, 192.0 * opt.N / ms / 1e6),
+      "| lib", os.environ.get("L2O_LIB", "default"))
