@@ -326,7 +326,18 @@ def main():
     dev = torch.device("cuda", local)
     distributed = world > 1
     if distributed:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; keep stdout = the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     desc, dcoords, dT, netkind = WORKLOADS[args.workload]
     coords = args.coords or dcoords
