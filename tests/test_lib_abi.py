@@ -55,3 +55,20 @@ def test_product_package_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|import_module\([\"']oracle|oracle[./]l2o_oracle", src, re.M), f
+
+
+def test_hrnn_abi_without_gpu():
+    """HierarchicalRNN entry points: constants and argument validation happen before any CUDA call."""
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    L = _lib.lib()
+    assert L.l2o_hrnn_theta_count() == 8349 and L.l2o_hrnn_state_floats() == 21
+    h = ctypes.c_void_p()
+    assert L.l2o_hrnn_create(ctypes.byref(h), None, 3) == _lib.L2O_E_INVALID
+    sizes = (ctypes.c_int64 * 2)(5, 0)
+    assert L.l2o_hrnn_create(ctypes.byref(h), sizes, 2) == _lib.L2O_E_INVALID       # empty tensor
+    assert L.l2o_hrnn_workspace_bytes(None) == _lib.L2O_E_INVALID
+    assert L.l2o_hrnn_step(None, None, None) == _lib.L2O_E_INVALID
+    from open_l2o_b200.hierarchical_rnn import THETA_SPEC
+    import math
+    assert sum(math.prod(s) for _, s in THETA_SPEC) == 8349
