@@ -216,7 +216,7 @@ def quick_measure_hrnn(steps, warmup, T=20, batch=128):
            "coords": n, "unroll": T, "mode": "infer (optimizer step; meta-training of the HierarchicalRNN not built)",
            "regime": "external-gradient (torch autograd ConvNet forward/backward between l2o_hrnn_step calls, eager)",
            "value": n * T * steps / t, "unit": "coordinate-updates/s", "ms_per_step": 1e3 * t / steps, "steps": steps,
-           "warmup": warmup, "gpu_launches": launches, "last_fx": float(loss),
+           "warmup": warmup, "gpu_launches": launches, "last_fx": float(loss.detach()),
            "optimizer_step_us": 1e6 * t_step}
     del opt, params
     # HBM roofline of the step on a state that does not fit L2: 16 tensors x 2M coordinates

@@ -463,6 +463,19 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
   for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
     const int64_t i = pair * kTileCoords + tile * 128 + row;
     const bool act = i < n;
+    {  // pull the NEXT pair's state rows towards L2: with T = 1 (l2o_step) the loads below are the critical path
+      const int64_t inx = i + (int64_t)gridDim.x * kTileCoords;
+      if (inx < n) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state + inx * kH + U0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state + (n + inx) * kH + U0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state + 2 * n * kH + inx * kH + U0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state + 2 * n * kH + (n + inx) * kH + U0));
+        if (HALF == 1) {
+          if (a.x) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x + inx));
+          if (!in_kernel_opt) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.in_seq + inx));
+        }
+      }
+    }
     float c1[NU], c2[NU];
     float x = 0.f, oa = 0.f, ob = 0.f;
     {

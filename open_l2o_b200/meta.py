@@ -229,22 +229,31 @@ class _Program(object):
         self.unroll_idx = 0
 
     # ---- optimizee evaluation --------------------------------------------------------------------
-    def _loss_at(self, Xflat):
+    def _var_views(self, Xflat):
+        """The optimizee variables as views of the flat arena (creation order)."""
+        out = []
+        for j, v in enumerate(self.variables):
+            n = int(np.prod(v["shape"])) if v["shape"] else 1
+            o = self.var_off[j]
+            out.append(Xflat[o:o + n].view(v["shape"]))
+        return out
+
+    def _loss_from_vars(self, var_list):
         """_make_with_custom_variables (DM/meta.py:131-155): trainables popped in creation order."""
         queue = collections.deque(range(len(self.variables)))
 
         def getter(name, shape, dtype, initializer, trainable):
             if trainable:
-                j = queue.popleft()
-                n = int(np.prod(shape)) if shape else 1
-                o = self.var_off[j]
-                return Xflat[o:o + n].view(shape)
+                return var_list[queue.popleft()]
             return self.const_vals[name]
 
-        if self.scale_active:
-            Xflat = Xflat * self.scale_flat
+        if self.scale_active:   # x (.) scale of the enhanced recipe (DM/meta_dm_train.py:336-338,384-385)
+            var_list = [v * sc for v, sc in zip(var_list, self._var_views(self.scale_flat))]
         with variable_getter(getter):
             return self.make_loss()
+
+    def _loss_at(self, Xflat):
+        return self._loss_from_vars(self._var_views(Xflat))
 
     def _apply_scale_feed(self, feed):
         fed = [p for p in self.scale_placeholders if p in feed]
@@ -273,13 +282,19 @@ class _Program(object):
                 .reshape(v["shape"]).cpu().numpy() for j, v in enumerate(self.variables)]
 
     def _value_and_grad(self, Xflat):
-        Xl = Xflat.detach().requires_grad_(True)
+        """f(x) and df/dx as a flat [N] tensor.  Each variable is its own autograd leaf (a view of the arena), so the
+        backward pass produces one gradient per variable and never materialises zero-filled [N] tensors."""
+        leaves = [v.detach().requires_grad_(True) for v in self._var_views(Xflat)]
         with torch.enable_grad():
-            fx = self._loss_at(Xl)
-            (g,) = torch.autograd.grad(fx, Xl, allow_unused=True)
-        if g is None:
-            g = torch.zeros_like(Xl)
-        return fx.detach(), g.contiguous()
+            fx = self._loss_from_vars(leaves)
+            grads = torch.autograd.grad(fx, leaves, allow_unused=True)
+        g = torch.empty_like(Xflat)
+        for gv, gj in zip(self._var_views(g), grads):
+            if gj is None:
+                gv.zero_()
+            else:
+                gv.copy_(gj)
+        return fx.detach(), g
 
     # ---- the unroll --------------------------------------------------------------------------------
     def _step0(self, feed):
