@@ -60,7 +60,8 @@ WORKLOADS = {
             1004105, 20, "dm_logsign"),
     "rnnprop_mlp": ("L2O-RNNProp, MLP 784-100-10 synthetic batch 128, unroll=20 (BASELINE config #3)", 79510, 20,
                     "rnnprop"),
-    "quadratic": ("L2O-DM, quadratic 128x10, unroll=20 (BASELINE config #1)", 1280, 20, "dm_identity"),
+    "quadratic": ("L2O-DM, quadratic 128x10, unroll=20 (BASELINE config #1; dense W_b x_b evaluated in-kernel)", 1280,
+                  20, "dm_identity"),
 }
 
 
@@ -395,7 +396,7 @@ def main():
     r = prog.runs[0]
     h = r.net.handle
     roof = None
-    if prog.fused is not None:
+    if prog.fused is not None and args.workload == "rastrigin":
         fw, bw = [], []
         for _ in range(max(2, min(args.steps, 3))):
             prog.fx_buf.zero_()
@@ -445,7 +446,7 @@ def main():
 
     # ---- infer mode (evaluate_dm.py: forward unroll only, no checkpoints) -----------------------------
     infer = None
-    if prog.fused is not None:
+    if prog.fused is not None and args.workload == "rastrigin":
         ts = []
         for _ in range(max(2, min(args.steps, 3))):
             xw = prog.X.clone()
@@ -488,7 +489,7 @@ def main():
         if distributed:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e = {"value": coords * world * T * args.steps / float(t_e.item()), "unit": "coordinate-updates/s",
-               "h2d_bytes_per_step": 3 * 4 * coords, "d2h_bytes_per_step": 4 * coords + 8}
+               "h2d_bytes_per_step": 4 * (hx.numel() + ha.numel() + hb.numel()), "d2h_bytes_per_step": 4 * coords + 8}
     else:
         e2e = {"value": value, "unit": "coordinate-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
                "note": "external-gradient workload: optimizee tensors are device-resident by construction"}

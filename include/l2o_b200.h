@@ -55,6 +55,9 @@ extern "C" {
 #define L2O_OPT_NONE 0
 #define L2O_OPT_RASTRIGIN_SEP 1  /* f = fscale*sum(0.5(x-a)^2 - alpha*b*cos(2 pi x) + alpha)   DM/problems.py:177-213, A=I */
 #define L2O_OPT_QUADRATIC_DIAG 2 /* f = fscale*sum((a*x-b)^2)                                   DM/problems.py:73-101, W diagonal */
+#define L2O_OPT_QUADRATIC_BATCH 3 /* f = fscale*sum_b ||W_b x_b - y_b||^2, dense W_b [d,d] per group of d = opt_group
+                                     consecutive coordinates; opt_a = W [n/d][d][d], opt_b = y [n]; exact-fp32 engine
+                                     (groups exchange x through shared memory)                   DM/problems.py:73-101 */
 
 #define L2O_ENGINE_AUTO 0
 #define L2O_ENGINE_FFMA 1   /* exact-fp32 CUDA-core kernels */
@@ -115,6 +118,7 @@ typedef struct {
   const float* labels;  /* optional [T][n]: imitation targets      DM/meta_dm_train.py:472-475 */
   double* imit_loss;    /* += sum_t 0.5*sum((label-delta)^2)/n_total */
   int64_t n_total;
+  int32_t opt_group;    /* L2O_OPT_QUADRATIC_BATCH: coordinates per dense group (1..128, n % opt_group == 0) */
 } l2o_unroll_args;
 
 typedef struct {

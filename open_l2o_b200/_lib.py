@@ -18,7 +18,7 @@ INCLUDE = os.path.join(_ROOT, "include")
 
 L2O_OK, L2O_E_INVALID, L2O_E_UNSUPPORTED, L2O_E_CUDA, L2O_E_NOMEM = 0, -1, -2, -3, -4
 PRE_IDENTITY, PRE_LOGSIGN, PRE_FC = 0, 1, 2
-OPT_NONE, OPT_RASTRIGIN_SEP, OPT_QUADRATIC_DIAG = 0, 1, 2
+OPT_NONE, OPT_RASTRIGIN_SEP, OPT_QUADRATIC_DIAG, OPT_QUADRATIC_BATCH = 0, 1, 2, 3
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
 
 # every symbol include/l2o_b200.h declares (tests check the .so exports all of them)
@@ -51,7 +51,7 @@ class UnrollArgs(C.Structure):
                 ("opt_a", _fp), ("opt_b", _fp), ("opt_alpha", C.c_float), ("opt_fscale", C.c_float), ("x", _fp),
                 ("state", _fp), ("ckpt", _fp), ("m", _fp), ("v", _fp), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("step0", C.c_int32), ("g_rec", _fp), ("feat_rec", _fp), ("fx", _fp), ("delta_seq", _fp),
-                ("labels", _fp), ("imit_loss", _fp), ("n_total", C.c_int64)]
+                ("labels", _fp), ("imit_loss", _fp), ("n_total", C.c_int64), ("opt_group", C.c_int32)]
 
 
 class BwdArgs(C.Structure):

@@ -199,6 +199,37 @@ __global__ void __launch_bounds__(kTile) step_kernel(l2o_step_args a, NetRt rt) 
 // ------------------------------------------------------------------------------------------
 // K2: fused T-step unroll; state in registers for all T steps.
 // ------------------------------------------------------------------------------------------
+// L2O_OPT_QUADRATIC_BATCH (DM/problems.py:73-101): f = fscale * sum_b ||W_b x_b - y_b||^2 with a dense W_b [d,d] per
+// group of d consecutive coordinates; g = 2 fscale W_b^T (W_b x_b - y_b).  Called by every thread of the CTA: the group
+// members exchange x, then the residuals, through shared memory.  Thread = coordinate k of group b owns residual row k.
+__device__ __forceinline__ void quadratic_batch_eval(const l2o_unroll_args& a, int gd, bool act, int64_t i, float x,
+                                                     float* sX, float* sR, float& f, float& g) {
+  const int tid = threadIdx.x;
+  sX[tid] = x;
+  __syncthreads();
+  float r = 0.f;
+  int k = 0, t0 = 0;
+  if (act) {
+    k = (int)(i % gd);
+    t0 = tid - k;  // first thread of this group inside the tile
+    const float* __restrict__ wrow = a.opt_a + i * gd;   // W[b][k][:]
+    float acc = 0.f;
+    for (int j = 0; j < gd; ++j) acc = fmaf(wrow[j], sX[t0 + j], acc);
+    r = acc - a.opt_b[i];
+  }
+  sR[tid] = r;
+  __syncthreads();
+  f = 0.f;
+  g = 0.f;
+  if (act) {
+    const float* __restrict__ wcol = a.opt_a + (i - k) * gd + k;  // W[b][:][k], stride d
+    float acc = 0.f;
+    for (int j = 0; j < gd; ++j) acc = fmaf(wcol[(int64_t)j * gd], sR[t0 + j], acc);
+    g = a.opt_fscale * (2.0f * acc);
+    f = a.opt_fscale * (r * r);
+  }
+}
+
 template <class C>
 __global__ void __launch_bounds__(kTile) unroll_fwd_kernel(l2o_unroll_args a, NetRt rt) {
   extern __shared__ __align__(16) float smem[];
@@ -207,6 +238,12 @@ __global__ void __launch_bounds__(kTile) unroll_fwd_kernel(l2o_unroll_args a, Ne
   const int T = a.T;
   const bool in_kernel_opt = a.opt_kind != L2O_OPT_NONE;
   const bool want_fx = in_kernel_opt && a.fx != nullptr;
+  // dense grouped optimizee (L2O_OPT_QUADRATIC_BATCH): the d coordinates of a group exchange x and residuals through
+  // shared memory, so a tile holds whole groups only
+  const bool grouped = a.opt_kind == L2O_OPT_QUADRATIC_BATCH;
+  const int gd = grouped ? a.opt_group : 1;
+  const int tile_n = grouped ? (kTile / gd) * gd : kTile;
+  __shared__ float sXg[kTile], sRg[kTile];
   if (want_fx)
     for (int t = threadIdx.x; t <= T; t += blockDim.x) sFx[t] = 0.0;
   stage_theta<C>(sT, a.theta);
@@ -214,23 +251,29 @@ __global__ void __launch_bounds__(kTile) unroll_fwd_kernel(l2o_unroll_args a, Ne
   const int64_t slot = n * C::SF;
   const int lane = threadIdx.x & 31;
   double imit = 0.0;
-  for (int64_t tile = blockIdx.x; tile * kTile < n; tile += gridDim.x) {
-    const int64_t i = tile * kTile + threadIdx.x;
-    const bool act = i < n;
+  for (int64_t tile = blockIdx.x; tile * tile_n < n; tile += gridDim.x) {
+    const int64_t i = tile * tile_n + threadIdx.x;
+    const bool act = (int)threadIdx.x < tile_n && i < n;
     CoordState<C> s;
     float x = 0.f, oa = 0.f, ob = 0.f, m = 0.f, v = 0.f;
     if (act) {
       s.load(a.state, n, i);
       if (a.ckpt) s.store(a.ckpt, n, i);
       if (a.x) x = a.x[i];
-      if (in_kernel_opt) { oa = a.opt_a[i]; ob = a.opt_b[i]; }
+      if (in_kernel_opt && !grouped) { oa = a.opt_a[i]; ob = a.opt_b[i]; }
       if (a.m) { m = a.m[i]; v = a.v[i]; }
     }
     for (int t = 0; t < T; ++t) {
       float fval = 0.f;
+      float fq = 0.f, gq = 0.f;
+      if (grouped) quadratic_batch_eval(a, gd, act, i, x, sXg, sRg, fq, gq);   // block-wide (two barriers)
       if (act) {
         float raw0, raw1 = 0.f;
-        if (in_kernel_opt) {
+        if (grouped) {
+          fval = fq;
+          raw0 = gq;
+          if (a.g_rec) a.g_rec[(int64_t)t * n + i] = raw0;
+        } else if (in_kernel_opt) {
           optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, raw0);
           if (a.g_rec) a.g_rec[(int64_t)t * n + i] = raw0;
         } else if (C::NIN == 2 && a.m == nullptr) {
@@ -263,8 +306,13 @@ __global__ void __launch_bounds__(kTile) unroll_fwd_kernel(l2o_unroll_args a, Ne
       }
     }
     float fval = 0.f;
+    float fqT = 0.f, gqT = 0.f;
+    if (grouped) quadratic_batch_eval(a, gd, act, i, x, sXg, sRg, fqT, gqT);
     if (act) {
-      if (in_kernel_opt) {
+      if (grouped) {
+        fval = fqT;
+        if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gqT;
+      } else if (in_kernel_opt) {
         float gT;
         optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, gT);
         if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gT;

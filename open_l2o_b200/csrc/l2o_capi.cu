@@ -139,7 +139,9 @@ int l2o_step(l2o_handle h, const l2o_step_args* a, void* stream) {
 int l2o_unroll_fwd(l2o_handle h, const l2o_unroll_args* a, void* stream) {
   if (!h || !a || a->n < 0 || a->T < 0 || !a->theta) return L2O_E_INVALID;
   if (a->opt_kind == L2O_OPT_NONE && !a->in_seq && a->T > 0) return L2O_E_INVALID;
-  if (a->opt_kind < L2O_OPT_NONE || a->opt_kind > L2O_OPT_QUADRATIC_DIAG) return L2O_E_INVALID;
+  if (a->opt_kind < L2O_OPT_NONE || a->opt_kind > L2O_OPT_QUADRATIC_BATCH) return L2O_E_INVALID;
+  if (a->opt_kind == L2O_OPT_QUADRATIC_BATCH &&
+      (a->opt_group < 1 || a->opt_group > 128 || a->n % a->opt_group != 0)) return L2O_E_INVALID;
   if (a->opt_kind != L2O_OPT_NONE && (!a->x || !a->opt_a || !a->opt_b)) return L2O_E_INVALID;
   if (a->opt_kind != L2O_OPT_NONE && h->desc.n_in == 2 && !a->m) return L2O_E_INVALID;
   if (h->state_floats > 0 && !a->state) return L2O_E_INVALID;

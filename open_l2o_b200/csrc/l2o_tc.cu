@@ -6,7 +6,9 @@
 
 namespace l2o {
 bool tc_supported(int cfg) { return cfg == 0 || cfg == 1; }  // LSTM-20x2 with identity / LogAndSign preprocessing
-bool tc_fwd_ok(const l2o_unroll_args& a) { return a.m == nullptr && a.feat_rec == nullptr; }
+bool tc_fwd_ok(const l2o_unroll_args& a) {  // grouped optimizees exchange x across coordinates: exact-fp32 engine only
+  return a.m == nullptr && a.feat_rec == nullptr && a.opt_kind != L2O_OPT_QUADRATIC_BATCH;
+}
 bool tc_auto_default() { return true; }
 bool tc_bwd_auto_default() { return true; }  // parity-green on the B200 (tests/test_tc_gpu.py)
 

@@ -9,10 +9,11 @@ import torch
 
 from . import _lib
 from ._lib import (BwdArgs, NetDesc, StepArgs, UnrollArgs, L2OError, PRE_FC, PRE_IDENTITY, PRE_LOGSIGN,
-                   OPT_NONE, OPT_QUADRATIC_DIAG, OPT_RASTRIGIN_SEP, ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC)
+                   OPT_NONE, OPT_QUADRATIC_DIAG, OPT_RASTRIGIN_SEP, OPT_QUADRATIC_BATCH, ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC)
 
 _PRE = {"identity": PRE_IDENTITY, "LogAndSign": PRE_LOGSIGN, "fc": PRE_FC}
-OPT_KINDS = {"rastrigin_sep": OPT_RASTRIGIN_SEP, "quadratic_diag": OPT_QUADRATIC_DIAG}
+OPT_KINDS = {"rastrigin_sep": OPT_RASTRIGIN_SEP, "quadratic_diag": OPT_QUADRATIC_DIAG,
+             "quadratic_batch": OPT_QUADRATIC_BATCH}
 
 
 def _ptr(t: Optional[torch.Tensor], dtype=torch.float32, name="tensor"):
@@ -113,7 +114,7 @@ class NetHandle:
     def unroll_fwd(self, theta, n, T, state, *, in_seq=None, opt_kind=OPT_NONE, opt_a=None, opt_b=None,
                    opt_alpha=10.0, opt_fscale=1.0, x=None, ckpt=None, m=None, v=None, beta1=0.95, beta2=0.95,
                    step0=1, g_rec=None, feat_rec=None, fx=None, delta_seq=None, labels=None, imit_loss=None,
-                   n_total=0):
+                   n_total=0, opt_group=0):
         a = UnrollArgs()
         a.n, a.T = n, T
         a.theta = _ptr(theta, name="theta")
@@ -129,6 +130,7 @@ class NetHandle:
         a.delta_seq, a.labels = _ptr(delta_seq, name="delta_seq"), _ptr(labels, name="labels")
         a.imit_loss = _ptr(imit_loss, torch.float64, "imit_loss")
         a.n_total = n_total
+        a.opt_group = opt_group
         _lib.check(_lib.lib().l2o_unroll_fwd(self._h, C.byref(a), _stream()), "l2o_unroll_fwd")
 
     def unroll_bwd(self, theta, n, T, in_seq, ckpt, dtheta, *, g_rec=None, labels=None, n_total=0, delta_seq=None):

@@ -318,7 +318,7 @@ class _Program(object):
         h.unroll_fwd(r.net.theta, r.n, T, work_state, opt_kind=_engine.OPT_KINDS[f.kind],
                      opt_a=self.const_vals[f.a].reshape(-1), opt_b=self.const_vals[f.b].reshape(-1),
                      opt_alpha=f.alpha, opt_fscale=f.fscale, x=r.x_work, ckpt=r.ckpt if train else None,
-                     g_rec=r.g_rec, fx=self.fx_buf, **kw)
+                     g_rec=r.g_rec, fx=self.fx_buf, opt_group=getattr(f, "group", 0), **kw)
         del state
         r.state_final = work_state
         return self.fx_buf

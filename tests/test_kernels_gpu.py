@@ -294,3 +294,44 @@ def test_unsupported_shape_is_rejected_loudly():
     h = make_handle(SPECS["dm_identity"])
     with pytest.raises(L2OError):
         h.step(torch.zeros(h.n_theta), torch.zeros(4), torch.zeros(320), torch.zeros(320))  # CPU tensors
+
+
+@pytest.mark.parametrize("B,d", [(128, 10), (37, 7), (3, 128), (50, 1)])
+def test_unroll_fused_quadratic_batch(B, d):
+    """L2O_OPT_QUADRATIC_BATCH (BASELINE config #1's optimizee, DM/problems.py:73-101): dense W_b x_b evaluated
+    in-kernel with the group's x exchanged through shared memory — forward unroll + recorded gradients + BPTT
+    against the oracle's autograd through the same unroll.  Group sizes that do / do not divide the 128-thread tile."""
+    from open_l2o_b200.engine import OPT_KINDS
+    spec = SPECS["dm_identity"]
+    n, T = B * d, 12
+    gen = torch.Generator().manual_seed(7)
+    theta = _theta(spec, gain=0.05)
+    w = torch.rand(B, d, d, generator=gen)
+    y = torch.rand(B, d, generator=gen)
+    x0 = torch.randn(n, generator=gen) * 0.01
+    f32 = lambda x: orc.quadratic_f(x.reshape(B, d), w, y)
+    f64 = lambda x: orc.quadratic_f(x.reshape(B, d), w.double(), y.double())
+    g32, res32 = orc.meta_grad(spec, theta, x0, orc.initial_state(spec, n), f32, T)
+    g64, res64 = orc.meta_grad(spec, theta.double(), x0.double(), orc.initial_state(spec, n, torch.float64), f64, T)
+    h = make_handle(spec)
+    sf = h.state_floats
+    th = theta.to(DEV)
+    arena = h.new_state(n, DEV)
+    ckpt = torch.zeros((T + 1) * sf * n, device=DEV)
+    x = x0.to(DEV).clone()
+    g_rec = torch.empty(T + 1, n, device=DEV)
+    fx = torch.zeros(T + 1, dtype=torch.float64, device=DEV)
+    h.unroll_fwd(th, n, T, arena, opt_kind=OPT_KINDS["quadratic_batch"], opt_a=w.reshape(-1).to(DEV),
+                 opt_b=y.reshape(-1).to(DEV), opt_fscale=1.0 / B, opt_group=d, x=x, ckpt=ckpt, g_rec=g_rec, fx=fx)
+    torch.cuda.synchronize()
+    slack = max(REL_TOL, 3.0 * rel_err(res32.x_final, res64.x_final))
+    assert rel_err(fx, res64.fx) <= slack
+    assert rel_err(x, res64.x_final) <= slack
+    dtheta = torch.zeros(h.n_theta, dtype=torch.float64, device=DEV)
+    h.unroll_bwd(th, n, T, g_rec, ckpt, dtheta, g_rec=g_rec)
+    torch.cuda.synchronize()
+    gslack = max(REL_TOL, 3.0 * rel_err(g32, g64))
+    assert rel_err(dtheta, g64) <= gslack, (rel_err(dtheta, g64), rel_err(g32, g64))
+    with pytest.raises(Exception):   # a group must not straddle the problem
+        h.unroll_fwd(th, n, T, arena, opt_kind=OPT_KINDS["quadratic_batch"], opt_a=w.reshape(-1).to(DEV),
+                     opt_b=y.reshape(-1).to(DEV), opt_fscale=1.0 / B, opt_group=d + 1 if n % (d + 1) else 0, x=x)

@@ -331,3 +331,27 @@ def test_data_loader_and_run_epoch_branches():
     t, cost = util.run_epoch(sess, ms.fx, [ms.update, ms.step], ms.reset, 2, scale=scale, rd_scale=True,
                              assign_func=optimizer.assign_func, var_x=var_x)
     assert np.isfinite(cost)
+
+
+def test_training_quadratic_fused_dense_groups():
+    """problems.quadratic at a batch large enough for the fused regime: the dense per-group gradient is evaluated
+    in-kernel (L2O_OPT_QUADRATIC_BATCH); two training unrolls against the oracle's autograd trainer."""
+    from open_l2o_b200 import meta, problems
+    B, d, T = 2048, 10, 6
+    problem = problems.quadratic(batch_size=B, num_dims=d)
+    optimizer = meta.MetaOptimizer(cw={"net": "CoordinateWiseDeepLSTM", "net_options": {"layers": (20, 20)}})
+    ms = optimizer.meta_minimize(problem, T, learning_rate=0.001)
+    prog = optimizer.program
+    assert prog.fused is not None and prog.fused.kind == "quadratic_batch"
+    sess = meta.Session()
+    sess.run(ms.reset)
+    w, y = prog.const_vals["w"].cpu(), prog.const_vals["y"].cpu()
+    spec = orc.NetSpec(layers=(20, 20))
+    tr = _oracle_trainer_for(prog, spec, 0.001, f=lambda x: orc.quadratic_f(x, w, y))
+    tr.reset(prog.X.cpu().clone().reshape(B, d))
+    for it in range(2):
+        cost, xs, _, _ = sess.run([ms.fx, ms.x, ms.update, ms.step])
+        res = tr.run_unroll(T)
+        assert abs(cost - float(res.fx[-1])) <= 1e-5 * abs(float(res.fx[-1])) + 1e-9
+        assert rel_err(xs[0], res.x_final) <= REL_TOL
+        assert rel_err(next(iter(prog.nets.values())).theta, tr.theta) <= 5e-5, it
