@@ -238,16 +238,6 @@ __device__ __forceinline__ void store_units(float* __restrict__ p, const float* 
     else *reinterpret_cast<float2*>(p + K0) = make_float2(v[K0], v[K0 + 1]);
   });
 }
-// per-unit TMEM columns [col0, col0+NU) of this lane -> v (one wait for the three loads)
-template <int HALF>
-__device__ __forceinline__ void tmem_ld_units(uint32_t taddr, float* v) {
-  for_chunks<HALF>([&](auto k0c, auto ncc) {
-    L2O_CHUNK(K0, NC, k0c, ncc);
-    tmem_ldn<NC>(taddr + K0, v + K0);
-  });
-  tc_wait_ld();
-}
-
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -386,12 +376,6 @@ __device__ __forceinline__ void lstm_point_fwd(float zi, float zj, float zf, flo
   const float Eo = ex2_approx(fminf(-kLog2e * zo, 63.f));
   h = (1.0f - Ec) * rcp_approx((1.0f + Ec) * (1.0f + Eo));
 }
-// LSTM pointwise update of 4 hidden units from 16 accumulator columns (i,j,f,o interleaved).
-__device__ __forceinline__ void lstm_units4(const float* z, float* c, float* h) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) lstm_point_fwd(z[4 * u + 0], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3], c[u], h[u]);
-}
-
 // write 4 values (hi/lo split) to A_hi / A_lo columns [col, col+4)
 __device__ __forceinline__ void st_split4(uint32_t a_hi, uint32_t a_lo, int col, const float* v) {
   float h0, h1, h2, h3, l0, l1, l2, l3;
