@@ -116,3 +116,30 @@ def test_lambda_suffix_sum_identity():
         total = total + (lam * delta).sum()
     (g2,) = torch.autograd.grad(total, th)
     assert torch.allclose(g, g2, rtol=1e-4, atol=1e-7)
+
+
+def test_lstm_cell_agrees_with_an_independent_lstm_after_gate_relabelling():
+    """The oracle's cell against torch.nn.LSTMCell — an independent LSTM implementation whose documented gate order is
+    (i, f, g, o) with no built-in forget bias.  Relabelling the Sonnet-order columns (i, j, f, o) and moving the +1.0
+    forget bias into the bias vector must reproduce (h', c') exactly; this pins the arithmetic of the restatement
+    (what remains unpinned is only Sonnet's own column order / forget-bias convention, see the module header)."""
+    from oracle import l2o_oracle as orc
+    torch.manual_seed(0)
+    n, f, h = 7, 3, 5
+    x = torch.randn(n, f, dtype=torch.float64)
+    h0, c0 = torch.randn(n, h, dtype=torch.float64), torch.randn(n, h, dtype=torch.float64)
+    w = torch.randn(f + h, 4 * h, dtype=torch.float64) * 0.4       # Sonnet layout: rows [x | h], columns i|j|f|o
+    b = torch.randn(4 * h, dtype=torch.float64) * 0.1
+    h1, c1 = orc.lstm_cell(x, h0, c0, w, b)
+    cell = torch.nn.LSTMCell(f, h, dtype=torch.float64)
+    i_, j_, f_, o_ = (slice(k * h, (k + 1) * h) for k in range(4))
+    order = [i_, f_, j_, o_]                                         # torch rows: i, f, g(=j), o
+    with torch.no_grad():
+        cell.weight_ih.copy_(torch.cat([w[:f, s].t() for s in order], 0))
+        cell.weight_hh.copy_(torch.cat([w[f:, s].t() for s in order], 0))
+        bias = torch.cat([b[s] for s in order], 0)
+        bias[h:2 * h] += 1.0                                         # forget_bias=1.0, added at run time by snt.LSTM
+        cell.bias_ih.copy_(bias)
+        cell.bias_hh.zero_()
+        h_t, c_t = cell(x, (h0, c0))
+    assert torch.allclose(h1, h_t, atol=1e-12) and torch.allclose(c1, c_t, atol=1e-12)
