@@ -441,8 +441,9 @@ def main():
                                "ms": 1e3 * t_f, "coord_updates_per_s": r.n * T / t_f},
                 "bwd_ms": 1e3 * t_b, "bwd_coord_updates_per_s": r.n * T / t_b,
                 "alg_flop_per_coord_update": {"fwd": fl, "bwd": 2 * fl},
-                "notes": "fp32 parity => 3xTF32 (tf32 = 1/2 bf16 rate): a 100%-busy tensor pipe reads 1/6 of this peak; "
-                         "the activation pipe (~360 MUFU ops per coordinate-update) caps the path near 1.1e10 upd/s/GPU"}
+                "notes": "fp32 parity => 3xTF32 (tf32 = 1/2 bf16 rate): a 100%-busy tensor pipe reads 1/6 of this peak "
+                         "(ncu: tensor pipe 30% active in this kernel, 22% in the forward kernel); the activation pipe "
+                         "(320 MUFU ops per coordinate-update forward, 400 backward) caps the path near 1.4e10 upd/s/GPU"}
 
     # ---- infer mode (evaluate_dm.py: forward unroll only, no checkpoints) -----------------------------
     infer = None
