@@ -186,12 +186,11 @@ def quick_measure_hrnn(steps, warmup, T=20, batch=128):
     labels = torch.nn.functional.one_hot(torch.randint(10, (batch,), generator=gen), 10).float().to(dev)
     opt = hr.HierarchicalRNN(random_seed=0, **hr.metarun_flags())
 
-    def unroll():
-        for _ in range(T):
-            loss = prob.objective(params, data, labels)
-            grads = torch.autograd.grad(loss, params)
-            opt.apply_gradients(zip(grads, params))
-        return loss
+    def objective(*ps):
+        return prob.objective(list(ps), data, labels)
+
+    def unroll():   # the public call: T optimizer steps, objective values read back at the end
+        return opt.minimize(objective, params, T)[-1]
     for _ in range(warmup):
         unroll()
     torch.cuda.synchronize()
@@ -215,9 +214,10 @@ def quick_measure_hrnn(steps, warmup, T=20, batch=128):
     out = {"workload": "L2O-Scale HierarchicalRNN [10,20,20], ConvNet 3x32x32 [(3,3,32),(5,5,32)] synthetic batch %d, "
                        "unroll=%d (BASELINE config #4)" % (batch, T),
            "coords": n, "unroll": T, "mode": "infer (optimizer step; meta-training of the HierarchicalRNN not built)",
-           "regime": "external-gradient (torch autograd ConvNet forward/backward between l2o_hrnn_step calls, eager)",
+           "regime": "external-gradient (torch autograd ConvNet forward/backward between l2o_hrnn_step calls; one "
+                     "iteration captured as a CUDA graph by HierarchicalRNN.minimize)",
            "value": n * T * steps / t, "unit": "coordinate-updates/s", "ms_per_step": 1e3 * t / steps, "steps": steps,
-           "warmup": warmup, "gpu_launches": launches, "last_fx": float(loss.detach()),
+           "warmup": warmup, "gpu_launches": launches, "last_fx": float(loss),
            "optimizer_step_us": 1e6 * t_step}
     del opt, params
     # HBM roofline of the step on a state that does not fit L2: 16 tensors x 2M coordinates

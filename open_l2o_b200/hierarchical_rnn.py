@@ -300,13 +300,50 @@ class HierarchicalRNN(object):
         _lib.check(_lib.lib().l2o_hrnn_step(self._h, C.byref(self._args(True)), torch.cuda.current_stream().cuda_stream),
                    "l2o_hrnn_step")
 
-    def minimize(self, objective, var_list: Sequence[torch.Tensor], num_steps: int):
+    def minimize(self, objective, var_list: Sequence[torch.Tensor], num_steps: int, cuda_graph: Optional[bool] = None):
         """Convenience loop of the evaluation drivers (SC/metatest.py): num_steps x (objective, gradients, step).
-        Returns the list of objective values (one device->host read at the end)."""
-        objs = []
-        for _ in range(num_steps):
+        Returns the list of objective values (one device->host read at the end).
+
+        One iteration is ~50 tiny launches (the optimizee's forward/backward, the gradient copies, the three step
+        kernels) and nothing in it needs the host, so after two eager iterations (slot creation, library warm-up) one
+        iteration is captured into a CUDA graph and replayed (``cuda_graph=False`` or ``L2O_CUDA_GRAPH=0`` keeps
+        everything eager; a failed capture falls back to the same eager kernels with a warning)."""
+        import os
+        var_list = list(var_list)
+
+        def body():
             loss = objective(*var_list)
-            grads = torch.autograd.grad(loss, list(var_list))
-            objs.append(loss.detach())
+            grads = torch.autograd.grad(loss, var_list)
             self.apply_gradients(zip(grads, var_list))
+            return loss.detach()
+
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("L2O_CUDA_GRAPH", "1") != "0"
+        objs = []
+        n_eager = num_steps if (not cuda_graph or num_steps < 4) else 2
+        for _ in range(n_eager):
+            objs.append(body())
+        remaining = num_steps - n_eager
+        if remaining > 0:
+            key = (id(objective), tuple(id(v) for v in var_list))
+            if getattr(self, "_graph_key", None) != key:
+                try:
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        static_loss = body()
+                    self._graph, self._graph_loss, self._graph_key = graph, static_loss, key
+                except Exception as e:   # capture not possible for this objective: same kernels, eagerly
+                    import warnings
+                    warnings.warn("CUDA-graph capture of the HierarchicalRNN step failed (%r); staying eager" % (e,))
+                    torch.cuda.synchronize()
+                    self._graph_key = None
+                    for _ in range(remaining):
+                        objs.append(body())
+                    remaining = 0
+            from . import engine as _engine
+            for _ in range(remaining):
+                self._graph.replay()
+                _engine.note_graph_replay(3)   # the three l2o_hrnn_step kernels inside the graph
+                objs.append(self._graph_loss.clone())
         return [float(o) for o in torch.stack(objs).cpu()]

@@ -89,3 +89,19 @@ def test_hrnn_minimizes_a_quadratic():
     b = torch.randn(30, device=DEV).requires_grad_(True)
     objs = opt.minimize(lambda w, b: (w ** 2).sum() + (b ** 2).sum(), [w, b], 60)
     assert objs[-1] < objs[0]
+
+
+def test_hrnn_minimize_graph_replay_matches_eager():
+    """HierarchicalRNN.minimize captures one (objective, gradients, step) iteration as a CUDA graph; the objective
+    trajectory must equal the eager one."""
+    from open_l2o_b200 import hierarchical_rnn as hr
+    out = []
+    for use_graph in (False, True):
+        opt = hr.HierarchicalRNN(random_seed=0, **hr.metarun_flags())
+        gen = torch.Generator().manual_seed(5)
+        w = torch.randn(200, 20, generator=gen).to(DEV).requires_grad_(True)
+        b = torch.randn(20, generator=gen).to(DEV).requires_grad_(True)
+        t = torch.randn(64, 200, generator=gen).to(DEV)
+        out.append(opt.minimize(lambda w, b: ((t @ w + b) ** 2).mean(), [w, b], 12, cuda_graph=use_graph))
+    assert len(out[0]) == len(out[1]) == 12
+    assert max(abs(a - c) / (abs(a) + 1e-30) for a, c in zip(out[0], out[1])) <= 1e-6
