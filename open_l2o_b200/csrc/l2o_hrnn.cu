@@ -410,10 +410,11 @@ using namespace l2o::hrnn;
 
 struct l2o_hrnn {
   int nt;
-  int64_t n;
+  int64_t n;         // local coordinates
+  int64_t n_global;  // problem-wide coordinate count the mean log-lr divides by (== n unless sharded)
   int nblocks;
   BlockEnt* d_blocks;
-  int64_t* d_sizes;
+  int64_t* d_sizes;  // per-tensor counts the per-tensor means divide by (global sizes when sharded)
 };
 
 extern "C" {
@@ -423,11 +424,11 @@ int l2o_hrnn_create(l2o_hrnn_handle* out, const int64_t* tensor_sizes, int32_t n
   int64_t n = 0;
   int64_t nb = 0;
   for (int j = 0; j < n_tensors; ++j) {
-    if (tensor_sizes[j] <= 0) return L2O_E_INVALID;
+    if (tensor_sizes[j] < 0) return L2O_E_INVALID;   // 0 = this rank holds no coordinate of tensor j (sharded use)
     n += tensor_sizes[j];
     nb += (tensor_sizes[j] + kBlock - 1) / kBlock;
   }
-  if (nb > 0x7fffffff) return L2O_E_INVALID;
+  if (nb > 0x7fffffff || n <= 0) return L2O_E_INVALID;
   BlockEnt* hb = new (std::nothrow) BlockEnt[nb];
   if (!hb) return L2O_E_NOMEM;
   int64_t b = 0, start = 0;
@@ -444,6 +445,7 @@ int l2o_hrnn_create(l2o_hrnn_handle* out, const int64_t* tensor_sizes, int32_t n
   if (!h) { delete[] hb; return L2O_E_NOMEM; }
   h->nt = n_tensors;
   h->n = n;
+  h->n_global = n;
   h->nblocks = (int)nb;
   h->d_blocks = nullptr;
   h->d_sizes = nullptr;
@@ -497,7 +499,9 @@ int l2o_hrnn_init_state(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream)
   return L2O_OK;
 }
 
-int l2o_hrnn_prepare(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
+// ---- phases.  Single-GPU: prepare = prepare_local + prepare_finish, step = step_local + step_finish.  Sharded: the
+// caller all-reduces the per-tensor sums (l2o_hrnn_reduce_layout) between the two phases.
+int l2o_hrnn_prepare_local(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
   int rc = check_args(h, a, false);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -506,13 +510,28 @@ int l2o_hrnn_prepare(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
   L2O_CUDA_TRY(cudaMemsetAsync(a->workspace, 0, bytes - align_up(sizeof(float) * (size_t)h->n, 256), st));
   scan_kernel<<<h->nblocks, kBlock, 0, st>>>(a->state, h->n, h->d_blocks, w);
   L2O_CUDA_TRY(cudaGetLastError());
-  tensor_kernel<<<1, 64, 0, st>>>(a->theta, a->layer, a->global, h->nt, h->d_sizes, h->n, w, 1);
-  L2O_CUDA_TRY(cudaGetLastError());
-  l2o::count_launch(2);
+  l2o::count_launch();
   return L2O_OK;
 }
 
-int l2o_hrnn_step(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
+int l2o_hrnn_prepare_finish(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
+  int rc = check_args(h, a, false);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve(w, a->workspace, h->nt, h->n);
+  tensor_kernel<<<1, 64, 0, st>>>(a->theta, a->layer, a->global, h->nt, h->d_sizes, h->n_global, w, 1);
+  L2O_CUDA_TRY(cudaGetLastError());
+  l2o::count_launch();
+  return L2O_OK;
+}
+
+int l2o_hrnn_prepare(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
+  int rc = l2o_hrnn_prepare_local(h, a, stream);
+  return rc ? rc : l2o_hrnn_prepare_finish(h, a, stream);
+}
+
+int l2o_hrnn_step_local(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
   int rc = check_args(h, a, true);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -520,11 +539,48 @@ int l2o_hrnn_step(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
   carve(w, a->workspace, h->nt, h->n);
   coord_kernel<<<h->nblocks, kBlock, 0, st>>>(a->theta, a->g, a->state, h->n, h->d_blocks, w);
   L2O_CUDA_TRY(cudaGetLastError());
-  tensor_kernel<<<1, 64, 0, st>>>(a->theta, a->layer, a->global, h->nt, h->d_sizes, h->n, w, 0);
+  l2o::count_launch();
+  return L2O_OK;
+}
+
+int l2o_hrnn_step_finish(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
+  int rc = check_args(h, a, true);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w;
+  carve(w, a->workspace, h->nt, h->n);
+  tensor_kernel<<<1, 64, 0, st>>>(a->theta, a->layer, a->global, h->nt, h->d_sizes, h->n_global, w, 0);
   L2O_CUDA_TRY(cudaGetLastError());
   apply_kernel<<<h->nblocks, kBlock, 0, st>>>(a->x, a->update, h->d_blocks, w);
   L2O_CUDA_TRY(cudaGetLastError());
-  l2o::count_launch(3);
+  l2o::count_launch(2);
+  return L2O_OK;
+}
+
+int l2o_hrnn_step(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
+  int rc = l2o_hrnn_step_local(h, a, stream);
+  return rc ? rc : l2o_hrnn_step_finish(h, a, stream);
+}
+
+int l2o_hrnn_set_global_sizes(l2o_hrnn_handle h, const int64_t* global_sizes) {
+  if (!h || !global_sizes) return L2O_E_INVALID;
+  int64_t tot = 0;
+  for (int j = 0; j < h->nt; ++j) {
+    if (global_sizes[j] <= 0) return L2O_E_INVALID;
+    tot += global_sizes[j];
+  }
+  L2O_CUDA_TRY(cudaMemcpy(h->d_sizes, global_sizes, sizeof(int64_t) * h->nt, cudaMemcpyHostToDevice));
+  h->n_global = tot;
+  return L2O_OK;
+}
+
+int l2o_hrnn_reduce_layout(l2o_hrnn_handle h, int64_t* n_doubles, int64_t* flags_offset_bytes, int64_t* n_flags) {
+  if (!h) return L2O_E_INVALID;
+  Workspace w;
+  carve(w, (void*)256, h->nt, h->n);   // offsets relative to a dummy non-null base
+  if (n_doubles) *n_doubles = (int64_t)h->nt * kAcc;
+  if (flags_offset_bytes) *flags_offset_bytes = (int64_t)((char*)w.any_nz - (char*)w.acc);
+  if (n_flags) *n_flags = (int64_t)h->nt * NS;
   return L2O_OK;
 }
 

@@ -37,3 +37,23 @@ def allreduce_meta_grad(dtheta: Dict[str, torch.Tensor], fx: torch.Tensor, group
     packed = pack(dtheta, fx)
     dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
     return unpack(packed, dtheta, fx)
+
+
+def allgather_shards(local: torch.Tensor, n: int, group=None) -> torch.Tensor:
+    """Reassemble a flat [n] tensor whose `shard_range` slices live on the ranks (slices differ by at most one element,
+    so every rank pads to the largest slice and one equal-size all-gather suffices).  Used by the sharded
+    HierarchicalRNN step to republish the updated optimizee parameters."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cap = (n + world - 1) // world
+    lo, hi = shard_range(n, rank, world)
+    assert local.numel() == hi - lo, (local.numel(), lo, hi)
+    buf = torch.zeros(cap, dtype=local.dtype, device=local.device)
+    buf[:hi - lo].copy_(local.reshape(-1))
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    parts = []
+    for r in range(world):
+        l, h = shard_range(n, r, world)
+        parts.append(out[r][:h - l])
+    return torch.cat(parts)

@@ -126,7 +126,7 @@ class HierarchicalRNN(object):
                  use_extreme_indicator=False, max_log_lr=33, obj_train_max_multiplier=-1, use_problem_lr_mean=False,
                  use_gradient_shortcut=False, use_lr_shortcut=False, use_grad_products=False,
                  use_multiple_scale_decays=False, learnable_inp_decay=True, learnable_rnn_init=True,
-                 random_seed=None, device="cuda", **kwargs):
+                 random_seed=None, device="cuda", distributed=False, **kwargs):
         # signature defaults = the reference's (HR:69-82); the drivers override three of them (metarun_flags())
         # argument checks of the reference (HR:132-144)
         if len(level_sizes) not in [1, 2, 3]:
@@ -167,6 +167,10 @@ class HierarchicalRNN(object):
         self.theta = theta.to(self.device)
         self._h = None
         self._vars: List[torch.Tensor] = []
+        # distributed=True: every rank holds a contiguous slice of every optimizee tensor's coordinates (the optimizee
+        # itself stays replicated); one small all-reduce of the per-tensor sums per step + an all-gather of the
+        # updated parameters.  Needs an initialised torch.distributed process group.
+        self.distributed = bool(distributed)
 
     # ---- variables (the TF variable collection of OPTIMIZER_SCOPE) ---------------------------------------------------
     def get_variables(self) -> Dict[str, torch.Tensor]:
@@ -188,21 +192,37 @@ class HierarchicalRNN(object):
     def _create_slots(self, var_list: Sequence[torch.Tensor]):
         """One slot set per optimizee tensor (trainable_optimizer.py:94-105), laid out as 21 planes over the
         concatenation of all tensors; the optimizee tensors become views of one flat arena."""
-        sizes = [int(v.numel()) for v in var_list]
-        if any(s <= 0 for s in sizes):
+        gsizes = [int(v.numel()) for v in var_list]
+        if any(s <= 0 for s in gsizes):
             raise ValueError("empty optimizee variable")
+        self.global_sizes = gsizes
+        if self.distributed:
+            import torch.distributed as tdist
+            from .dist import shard_range
+            self._rank, self._world = tdist.get_rank(), tdist.get_world_size()
+            self._ranges = [shard_range(n, self._rank, self._world) for n in gsizes]
+        else:
+            self._rank, self._world = 0, 1
+            self._ranges = [(0, n) for n in gsizes]
+        sizes = [hi - lo for lo, hi in self._ranges]
+        if sum(sizes) <= 0:
+            raise ValueError("this rank holds no coordinate (more ranks than coordinates)")
         arr = (C.c_int64 * len(sizes))(*sizes)
         h = C.c_void_p()
         _lib.check(_lib.lib().l2o_hrnn_create(C.byref(h), arr, len(sizes)), "l2o_hrnn_create")
         self._h, self.sizes, self.N = h, sizes, sum(sizes)
+        if self.distributed:
+            garr = (C.c_int64 * len(gsizes))(*gsizes)
+            _lib.check(_lib.lib().l2o_hrnn_set_global_sizes(h, garr), "l2o_hrnn_set_global_sizes")
         dev = self.device
         self.x = torch.empty(self.N, device=dev)
         self.g = torch.empty(self.N, device=dev)
         off = 0
-        for v in var_list:   # re-seat the variables on the arena (zero-copy flatten/unflatten afterwards)
-            n = v.numel()
-            self.x[off:off + n].copy_(v.detach().reshape(-1))
-            v.data = self.x[off:off + n].view(v.shape)
+        for v, (lo, hi) in zip(var_list, self._ranges):
+            n = hi - lo
+            self.x[off:off + n].copy_(v.detach().reshape(-1)[lo:hi])
+            if not self.distributed:   # re-seat the variables on the arena (zero-copy flatten/unflatten afterwards)
+                v.data = self.x[off:off + n].view(v.shape)
             off += n
         self._vars = list(var_list)
         self.state = torch.zeros(int(_lib.lib().l2o_hrnn_state_floats()), self.N, device=dev)
@@ -211,6 +231,13 @@ class HierarchicalRNN(object):
         nbytes = int(_lib.lib().l2o_hrnn_workspace_bytes(h))
         self.workspace = torch.zeros((nbytes + 255) // 4 + 64, dtype=torch.float32, device=dev)
         self.update = torch.empty(self.N, device=dev)
+        if self.distributed:   # views of the workspace head that the ranks all-reduce between the two step phases
+            nd, fo, nf = C.c_int64(), C.c_int64(), C.c_int64()
+            _lib.check(_lib.lib().l2o_hrnn_reduce_layout(h, C.byref(nd), C.byref(fo), C.byref(nf)), "l2o_hrnn_reduce_layout")
+            base = (self.workspace.data_ptr() + 255) // 256 * 256 - self.workspace.data_ptr()
+            raw = self.workspace.view(torch.uint8)
+            self._red_sums = raw[base:base + 8 * nd.value].view(torch.float64)
+            self._red_flags = raw[base + fo.value:base + fo.value + 4 * nf.value].view(torch.int32)
         self.reset_state()
 
     def __del__(self):
@@ -231,9 +258,19 @@ class HierarchicalRNN(object):
         a.update = _p(self.update)
         return a
 
+    def _allreduce_sums(self):
+        import torch.distributed as tdist
+        tdist.all_reduce(self._red_sums, op=tdist.ReduceOp.SUM)
+        tdist.all_reduce(self._red_flags, op=tdist.ReduceOp.MAX)
+
     def _prepare(self):
-        _lib.check(_lib.lib().l2o_hrnn_prepare(self._h, C.byref(self._args(False)), torch.cuda.current_stream().cuda_stream),
-                   "l2o_hrnn_prepare")
+        L, st, a = _lib.lib(), torch.cuda.current_stream().cuda_stream, self._args(False)
+        if not self.distributed:
+            _lib.check(L.l2o_hrnn_prepare(self._h, C.byref(a), st), "l2o_hrnn_prepare")
+            return
+        _lib.check(L.l2o_hrnn_prepare_local(self._h, C.byref(a), st), "l2o_hrnn_prepare_local")
+        self._allreduce_sums()
+        _lib.check(L.l2o_hrnn_prepare_finish(self._h, C.byref(a), st), "l2o_hrnn_prepare_finish")
 
     def reset_state(self, seed: Optional[int] = None, log_learning_rate: Optional[torch.Tensor] = None):
         """_initialize_state / _initialize_global_state (HR:303-350).  The log learning rates are drawn as in the
@@ -248,10 +285,10 @@ class HierarchicalRNN(object):
                 gen.manual_seed(int(s))
             lo, hi = math.log(self.init_lr_range[0]) / 2.0, math.log(self.init_lr_range[1]) / 2.0
             parts = []
-            for n in self.sizes:
+            for n, (slo, shi) in zip(self.global_sizes, self._ranges):   # drawn for the whole tensor, sliced per rank
                 actual = torch.rand(n, generator=gen) * (hi - lo) + lo
                 offset = torch.rand((), generator=gen) * (hi - lo) + lo
-                parts.append(torch.clamp(actual + offset, -33.0, 33.0))
+                parts.append(torch.clamp(actual + offset, -33.0, 33.0)[slo:shi])
             log_learning_rate = torch.cat(parts)
         self.state[12].copy_(torch.as_tensor(log_learning_rate, dtype=torch.float32).reshape(-1))
         self._prepare()
@@ -288,17 +325,28 @@ class HierarchicalRNN(object):
         elif len(pairs) != len(self._vars) or any(v is not w for (_, v), w in zip(pairs, self._vars)):
             raise ValueError("apply_gradients must be called with the variables the slots were created for")
         off = 0
-        for g, v in pairs:
-            n = v.numel()
-            self.g[off:off + n].copy_(g.reshape(-1))
+        for (g, v), (lo, hi) in zip(pairs, self._ranges):
+            n = hi - lo
+            self.g[off:off + n].copy_(g.reshape(-1)[lo:hi])
             off += n
         self.step_flat()
+        if self.distributed:   # republish the updated parameters to the replicated optimizee
+            from .dist import allgather_shards
+            off = 0
+            for (_, v), (lo, hi), n in zip(pairs, self._ranges, self.global_sizes):
+                v.data.copy_(allgather_shards(self.x[off:off + hi - lo], n).view(v.shape))
+                off += hi - lo
         return [v for _, v in pairs]
 
     def step_flat(self):
         """One step with the gradients already in ``self.g`` (flat arena order)."""
-        _lib.check(_lib.lib().l2o_hrnn_step(self._h, C.byref(self._args(True)), torch.cuda.current_stream().cuda_stream),
-                   "l2o_hrnn_step")
+        L, st, a = _lib.lib(), torch.cuda.current_stream().cuda_stream, self._args(True)
+        if not self.distributed:
+            _lib.check(L.l2o_hrnn_step(self._h, C.byref(a), st), "l2o_hrnn_step")
+            return
+        _lib.check(L.l2o_hrnn_step_local(self._h, C.byref(a), st), "l2o_hrnn_step_local")
+        self._allreduce_sums()
+        _lib.check(L.l2o_hrnn_step_finish(self._h, C.byref(a), st), "l2o_hrnn_step_finish")
 
     def minimize(self, objective, var_list: Sequence[torch.Tensor], num_steps: int, cuda_graph: Optional[bool] = None):
         """Convenience loop of the evaluation drivers (SC/metatest.py): num_steps x (objective, gradients, step).
@@ -319,6 +367,8 @@ class HierarchicalRNN(object):
 
         if cuda_graph is None:
             cuda_graph = os.environ.get("L2O_CUDA_GRAPH", "1") != "0"
+        if self.distributed:
+            cuda_graph = False   # the per-step collectives stay outside graph capture
         objs = []
         n_eager = num_steps if (not cuda_graph or num_steps < 4) else 2
         for _ in range(n_eager):

@@ -73,3 +73,27 @@ def test_sharded_meta_gradient_matches_unsharded(tmp_path):
     # Adam's first step is lr*sign(g): only entries with |g| above the sharding round-off can be compared exactly
     big = g.abs() > 1e-6 * den
     assert torch.allclose(got["theta"][big], th[big], atol=1e-6)
+
+
+def _gather_worker(rank, world, port, n, out):
+    from open_l2o_b200.dist import allgather_shards, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n, dtype=torch.float32) * 0.5 - 3.0
+    lo, hi = shard_range(n, rank, world)
+    got = allgather_shards(full[lo:hi].clone(), n)
+    assert torch.equal(got, full), (rank, got, full)
+    if rank == 0:
+        torch.save(got, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n", [1, 2, 7, 1000])
+def test_allgather_shards_reassembles_uneven_slices(tmp_path, n):
+    """Host logic of the sharded HierarchicalRNN step: uneven (and empty) shard_range slices padded to one equal-size
+    all-gather must give back the full tensor on every rank (gloo, world size 2)."""
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_gather_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
+    assert torch.equal(torch.load(out), torch.arange(n, dtype=torch.float32) * 0.5 - 3.0)

@@ -105,3 +105,18 @@ def test_hrnn_minimize_graph_replay_matches_eager():
         out.append(opt.minimize(lambda w, b: ((t @ w + b) ** 2).mean(), [w, b], 12, cuda_graph=use_graph))
     assert len(out[0]) == len(out[1]) == 12
     assert max(abs(a - c) / (abs(a) + 1e-30) for a, c in zip(out[0], out[1])) <= 1e-6
+
+
+def test_hrnn_sharded_step_matches_single_gpu():
+    """Coordinates of every tensor split over 2 ranks (one all-reduce of the per-tensor sums per step + an all-gather of
+    the updated parameters, scripts/hrnn_dist_check.py under torchrun) against the single-GPU optimizer."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "scripts", "hrnn_dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

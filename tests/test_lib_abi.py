@@ -65,8 +65,10 @@ def test_hrnn_abi_without_gpu():
     assert L.l2o_hrnn_theta_count() == 8349 and L.l2o_hrnn_state_floats() == 21
     h = ctypes.c_void_p()
     assert L.l2o_hrnn_create(ctypes.byref(h), None, 3) == _lib.L2O_E_INVALID
-    sizes = (ctypes.c_int64 * 2)(5, 0)
-    assert L.l2o_hrnn_create(ctypes.byref(h), sizes, 2) == _lib.L2O_E_INVALID       # empty tensor
+    sizes = (ctypes.c_int64 * 2)(5, -1)
+    assert L.l2o_hrnn_create(ctypes.byref(h), sizes, 2) == _lib.L2O_E_INVALID       # negative size
+    sizes = (ctypes.c_int64 * 2)(0, 0)
+    assert L.l2o_hrnn_create(ctypes.byref(h), sizes, 2) == _lib.L2O_E_INVALID       # no coordinate at all
     assert L.l2o_hrnn_workspace_bytes(None) == _lib.L2O_E_INVALID
     assert L.l2o_hrnn_step(None, None, None) == _lib.L2O_E_INVALID
     from open_l2o_b200.hierarchical_rnn import THETA_SPEC
