@@ -58,3 +58,21 @@ def test_global_state_sees_last_tensor_only():
     b = H.step(th, [ps[1], ps[0], ps[2]], [gs[1], gs[0], gs[2]], [sts[1], sts[0], sts[2]], g0)[2]
     c = H.step(th, [ps[0], ps[2], ps[1]], [gs[0], gs[2], gs[1]], [sts[0], sts[2], sts[1]], g0)[2]
     assert torch.allclose(a, b) and not torch.allclose(a, c)
+
+
+def test_constructor_argument_checks_need_no_gpu():
+    """The reference's argument errors (HR:132-144) and this build's flag-set check fire before any device work."""
+    import pytest
+    from open_l2o_b200 import hierarchical_rnn as hr
+    with pytest.raises(ValueError):
+        hr.HierarchicalRNN(level_sizes=[10, 20, 20, 5])
+    with pytest.raises(ValueError):
+        hr.HierarchicalRNN(level_sizes=[10, 20.0, 20])
+    with pytest.raises(ValueError):
+        hr.HierarchicalRNN(level_sizes=[10, 20, 20], init_lr_range=(1e-6,))
+    with pytest.raises(ValueError):
+        hr.HierarchicalRNN(level_sizes=[10, 20, 20], init_lr_range=(1e-2, 1e-6))
+    with pytest.raises(NotImplementedError):
+        hr.HierarchicalRNN(**dict(hr.metarun_flags(), use_attention=True))
+    flags = hr.metarun_flags()
+    assert flags["level_sizes"] == [10, 20, 20] and flags["use_problem_lr_mean"] and flags["num_gradient_scales"] == 4
