@@ -143,3 +143,17 @@ def test_lstm_cell_agrees_with_an_independent_lstm_after_gate_relabelling():
         cell.bias_hh.zero_()
         h_t, c_t = cell(x, (h0, c0))
     assert torch.allclose(h1, h_t, atol=1e-12) and torch.allclose(c1, c_t, atol=1e-12)
+
+
+def test_golden_lstm_vectors_match_their_generator():
+    """tests/golden/lstm_cell_hand.json is reproducible from its scalar-math generator (no torch, no oracle)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_lstm_cell_hand", os.path.join(GOLD, "make_lstm_cell_hand.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(GOLD, "lstm_cell_hand.json")) as f:
+        committed = json.load(f)
+    for got, want in zip(mod.regenerate(), committed):
+        for key in ("h_next", "c_next"):
+            for ra, rb in zip(got[key], want[key]):
+                assert all(abs(a - b) <= 1e-12 for a, b in zip(ra, rb)), (want["name"], key)
