@@ -8,7 +8,17 @@ import torch
 
 
 class data_loader(object):
-    def __init__(self, program, optimizers, unroll_len):
+    def __init__(self, *args):
+        """``data_loader(problem, var_x, constants, subsets, scale, optimizers, unroll_len)`` as the reference
+        (DM/data_generator.py:35-48; the program is reached through the ``var_x`` handles ``meta_minimize`` returned),
+        or the short form ``data_loader(program, optimizers, unroll_len)``."""
+        if len(args) == 7:
+            _problem, var_x, _constants, _subsets, _scale, optimizers, unroll_len = args
+            program = var_x[0]._prog
+        elif len(args) == 3:
+            program, optimizers, unroll_len = args
+        else:
+            raise TypeError("data_loader(problem, var_x, constants, subsets, scale, optimizers, unroll_len)")
         self.prog = program
         self.optimizers = optimizers.split(",") if isinstance(optimizers, str) else list(optimizers)
         self.unroll_len = unroll_len
@@ -24,7 +34,7 @@ class data_loader(object):
     def get_data(self, task_i, sess=None, num_unrolls=1, assign_func=None, rd_scale_bound=3.0, if_scale=True, mt_k=1):
         prog = self.prog
         name = self.optimizers[task_i]
-        prog.reset()                                              # sess.run(self.reset_x)
+        prog.reset_x()                                            # sess.run(self.reset_x): x + constants only
         feed = {}
         if if_scale:
             r_scale = [np.exp(np.random.uniform(-rd_scale_bound, rd_scale_bound, size=v["shape"])).astype(np.float32)

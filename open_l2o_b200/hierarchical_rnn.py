@@ -162,7 +162,17 @@ class HierarchicalRNN(object):
         self.device = torch.device(device)
         L = _lib.lib()
         self.n_theta = int(L.l2o_hrnn_theta_count())
-        theta = _init_theta(random_seed)
+        self.distributed = bool(distributed)
+        if random_seed is None:   # unseeded like the reference; the ranks of a sharded optimizer must draw the same theta
+            theta_seed = int(torch.seed() % (2 ** 31))
+            if self.distributed:
+                import torch.distributed as tdist
+                box = torch.tensor([theta_seed], dtype=torch.int64, device=self.device)
+                tdist.broadcast(box, src=0)
+                theta_seed = int(box.item())
+        else:
+            theta_seed = random_seed
+        theta = _init_theta(theta_seed)
         assert theta.numel() == self.n_theta
         self.theta = theta.to(self.device)
         self._h = None
@@ -281,8 +291,14 @@ class HierarchicalRNN(object):
         if log_learning_rate is None:
             gen = torch.Generator()
             s = self.random_seed if seed is None else seed
-            if s is not None:
-                gen.manual_seed(int(s))
+            if s is None:   # unseeded like the reference (a fresh draw per call); ranks must agree on it when sharded
+                s = int(torch.seed() % (2 ** 31))
+                if self.distributed:
+                    import torch.distributed as tdist
+                    box = torch.tensor([s], dtype=torch.int64, device=self.device)
+                    tdist.broadcast(box, src=0)
+                    s = int(box.item())
+            gen.manual_seed(int(s))
             lo, hi = math.log(self.init_lr_range[0]) / 2.0, math.log(self.init_lr_range[1]) / 2.0
             parts = []
             for n, (slo, shi) in zip(self.global_sizes, self._ranges):   # drawn for the whole tensor, sliced per rank
@@ -375,8 +391,14 @@ class HierarchicalRNN(object):
             objs.append(body())
         remaining = num_steps - n_eager
         if remaining > 0:
-            key = (id(objective), tuple(id(v) for v in var_list))
-            if getattr(self, "_graph_key", None) != key:
+            # The cache holds STRONG references to the objective and the variables and compares by identity: an id()
+            # recycled by the allocator after the old closure died can never alias a new objective.  Tensors the
+            # objective closes over are baked into the graph by address - update them in place between calls.
+            key = (objective, tuple(var_list))
+            old = getattr(self, "_graph_key", None)
+            same = (old is not None and old[0] is objective and len(old[1]) == len(var_list)
+                    and all(a is b for a, b in zip(old[1], var_list)))
+            if not same:
                 try:
                     torch.cuda.synchronize()
                     graph = torch.cuda.CUDAGraph()

@@ -213,14 +213,24 @@ class _Program(object):
                 r.feat_rec = torch.zeros(T, 2, r.n, device=self.device)
         self.fx_buf = torch.zeros(T + 1, dtype=torch.float64, device=self.device)
 
-    def reset(self):
-        """variables_initializer(state + x + constants) (DM/meta.py:378-383)."""
+    def reset_x(self):
+        """Re-run the initializers of x + constants only (``reset_x`` of DM/data_generator.py:50,80).  The tensors are
+        refilled IN PLACE: captured CUDA graphs and views handed out earlier keep pointing at live, current data."""
         for v, j in zip(self.variables, range(len(self.variables))):
             n = int(np.prod(v["shape"])) if v["shape"] else 1
             o = self.var_off[j]
             self.X[o:o + n].copy_(v["init"](v["shape"], self.gen).reshape(-1).to(self.device))
         for c in self.constants:
-            self.const_vals[c["name"]] = c["init"](c["shape"], self.gen).to(self.device, torch.float32).contiguous()
+            new = c["init"](c["shape"], self.gen).to(torch.float32).contiguous()
+            cur = self.const_vals.get(c["name"])
+            if cur is None or cur.shape != new.shape:
+                self.const_vals[c["name"]] = new.to(self.device)
+            else:
+                cur.copy_(new)
+
+    def reset(self):
+        """variables_initializer(state + x + constants) (DM/meta.py:378-383)."""
+        self.reset_x()
         for r in self.runs:
             r.state.zero_()
             if r.net.handle.n_in == 2:
@@ -501,14 +511,16 @@ class _MtTask(object):
                 raise NotImplementedError("imitation tasks need each net's variables contiguous in the arena")
             r = runs[0]
             h = r.net.handle
-            if h.n_in != 1:
-                raise NotImplementedError("imitation tasks are implemented for the L2O-DM nets")
             sf = h.state_floats
-            self.subsets.append(dict(run=r, n=r.n, state=h.new_state(r.n, prog.device),
-                                     ckpt=torch.zeros((T + 1) * max(sf * r.n, 1), device=prog.device),
-                                     dseq=torch.zeros(T * r.n, device=prog.device),
-                                     inp=Placeholder("mt{}_input_subset{}".format(index, len(self.subsets))),
-                                     lab=Placeholder("mt{}_label_subset{}".format(index, len(self.subsets)))))
+            sb = dict(run=r, n=r.n, state=h.new_state(r.n, prog.device),
+                      ckpt=torch.zeros((T + 1) * max(sf * r.n, 1), device=prog.device),
+                      dseq=torch.zeros(T * r.n, device=prog.device),
+                      inp=Placeholder("mt{}_input_subset{}".format(index, len(self.subsets))),
+                      lab=Placeholder("mt{}_label_subset{}".format(index, len(self.subsets))))
+            if h.n_in == 2:   # RNNProp: the task carries its own Adam moments (DM/meta_rnnprop_train.py:469-486)
+                sb.update(m=torch.zeros(r.n, device=prog.device), v=torch.zeros(r.n, device=prog.device),
+                          feat=torch.zeros(T, 2, r.n, device=prog.device))
+            self.subsets.append(sb)
         self.n_total = sum(sb["n"] for sb in self.subsets)
         self.adam = {k: dict(m=torch.zeros_like(net.theta), v=torch.zeros_like(net.theta), k=0)
                      for k, net in prog.nets.items()}
@@ -523,6 +535,9 @@ class _MtTask(object):
         if kinds == {"reset_mt"}:
             for sb in self.subsets:
                 sb["state"].zero_()
+                if "m" in sb:
+                    sb["m"].zero_()
+                    sb["v"].zero_()
             return {}
         train, commit = "step_mt" in kinds, "update_mt" in kinds
         self.il.zero_()
@@ -530,17 +545,30 @@ class _MtTask(object):
             for d in prog.dtheta.values():
                 d.zero_()
         finals = []
+        step0 = prog._step0(feed)
         for sb in self.subsets:
             r, n = sb["run"], sb["n"]
             h = r.net.handle
             inp, lab = self._dev(feed[sb["inp"]], T, n), self._dev(feed[sb["lab"]], T, n)
             work = sb["state"].clone()
+            if h.n_in == 2:
+                # RNNProp imitation unroll (DM/meta_rnnprop_train.py:505-534): raw gradients in, Adam features formed
+                # in-kernel from the task's own (m, v) with p = float(step + t), recorded for the backward sweep
+                mw, vw = sb["m"].clone(), sb["v"].clone()
+                h.unroll_fwd(r.net.theta, n, T, work, in_seq=inp, ckpt=sb["ckpt"] if train else None, labels=lab,
+                             imit_loss=self.il, n_total=self.n_total, m=mw, v=vw, beta1=prog.opt.beta1,
+                             beta2=prog.opt.beta2, step0=step0, feat_rec=sb["feat"])
+                if train:
+                    h.unroll_bwd(r.net.theta, n, T, sb["feat"], sb["ckpt"], prog.dtheta[r.key], labels=lab,
+                                 n_total=self.n_total)
+                finals.append((work, mw, vw))
+                continue
             h.unroll_fwd(r.net.theta, n, T, work, in_seq=inp, ckpt=sb["ckpt"] if train else None, labels=lab,
                          imit_loss=self.il, n_total=self.n_total, delta_seq=sb["dseq"] if train else None)
             if train:  # the recorded deltas let the tensor-core BPTT run in imitation mode too
                 h.unroll_bwd(r.net.theta, n, T, inp, sb["ckpt"], prog.dtheta[r.key], labels=lab, n_total=self.n_total,
                              delta_seq=sb["dseq"])
-            finals.append(work)
+            finals.append((work, None, None))
         out = {}
         if "loss_mt" in kinds:
             out["loss_mt:%d" % self.index] = float(self.il.item())
@@ -551,8 +579,11 @@ class _MtTask(object):
                 _engine.adam_step(net.theta, prog.dtheta[k], ad["m"], ad["v"], ad["k"], lr=prog.learning_rate)
             out["step_mt:%d" % self.index] = None
         if commit:
-            for sb, w in zip(self.subsets, finals):
+            for sb, (w, mw, vw) in zip(self.subsets, finals):
                 sb["state"].copy_(w)
+                if mw is not None:
+                    sb["m"].copy_(mw)
+                    sb["v"].copy_(vw)
             out["update_mt:%d" % self.index] = None
         return out
 
@@ -562,10 +593,14 @@ class MetaOptimizer(object):
     beta1 = 0.95
     beta2 = 0.95
 
-    def __init__(self, seed=0, distributed=False, **kwargs):
+    def __init__(self, **kwargs):
+        """``MetaOptimizer(**net_config)`` exactly as the reference (DM/meta.py:228): every keyword is a net id.  The
+        two engine-side knobs ride on underscore-prefixed names that cannot collide with a net id the reference's
+        drivers use: ``_seed`` (generator seed of the optimizee initializers, default 0) and ``_distributed``
+        (coordinates sharded over torch.distributed ranks, one all-reduce of [dtheta | fx] per meta-step)."""
         self._nets = None
-        self.seed = seed
-        self.distributed = distributed
+        self.seed = int(kwargs.pop("_seed", 0))
+        self.distributed = bool(kwargs.pop("_distributed", False))
         if not kwargs:
             # default coordinatewise network (DM/meta.py:244-255)
             self._config = {
@@ -596,10 +631,15 @@ class MetaOptimizer(object):
         return result
 
     def restore(self, sess, path, index):
-        """DM/meta_dm_train.py:290-302."""
+        """DM/meta_dm_train.py:290-302: load ``<net id>.l2l-<index>`` into the live nets (Adam slots are untouched,
+        exactly as the reference's assign ops leave them)."""
         for k, net in self._nets.items():
             with open(os.path.join(path, "{}.l2l-{}".format(k, index)), "rb") as f:
-                net.set_variables(networks._pickle.load(f))
+                data = networks._pickle.load(f)
+            for m, v, shp in net.variable_shapes():
+                if m not in data or v not in data[m] or tuple(np.shape(data[m][v])) != tuple(shp):
+                    raise ValueError("{}.l2l-{}: variable {}/{} missing or of the wrong shape".format(k, index, m, v))
+            net.set_variables(data)
 
     def meta_loss(self, make_loss, len_unroll, net_assignments=None, second_derivatives=False):
         """Returns ops computing the meta-loss (DM/meta.py:269-396)."""

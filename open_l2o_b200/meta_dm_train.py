@@ -57,8 +57,14 @@ class MetaOptimizer(_meta.MetaOptimizer):
         return (MetaStep(Op("step", self.program), *info[1:]),) + extras
 
     def restorer(self):
-        """DM/meta_dm_train.py:274-288: nothing to build in an eager engine."""
-        return None
+        """DM/meta_dm_train.py:274-288 builds one placeholder + assign op per net variable; an eager engine assigns
+        directly, so this only records (per net) the ``{module: {variable: shape}}`` map ``restore`` will check the
+        ``.l2l-<index>`` files against."""
+        self.restore_pl = {k: {m: {} for m, _, _ in net.variable_shapes()} for k, net in self._nets.items()}
+        for k, net in self._nets.items():
+            for m, v, shp in net.variable_shapes():
+                self.restore_pl[k][m][v] = tuple(shp)
+        return self.restore_pl
 
     def assign_func(self, values):
         self.program.assign_x(values)

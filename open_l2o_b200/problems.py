@@ -108,16 +108,29 @@ def rastrigin(batch_size=128, num_dims=10, alpha=10, stddev=1):
     return build
 
 
-def rastrigin_separable(num_dims=1000000, alpha=10.0, stddev=1.0, normalize=True):
+def rastrigin_separable(num_dims=1000000, alpha=10.0, stddev=1.0, normalize=True, shard=None):
     """The A = I member of DM/problems.py:177-213 with batch 1 - the only member that exists at d = 1e6
-    (a dense A would be 4 TB).  f = fscale * sum_i (0.5 (x_i-b_i)^2 - alpha c_i cos(2 pi x_i) + alpha)."""
+    (a dense A would be 4 TB).  f = fscale * sum_i (0.5 (x_i-b_i)^2 - alpha c_i cos(2 pi x_i) + alpha).
+
+    ``shard=(lo, hi)``: this rank's contiguous slice of the ``num_dims`` coordinates (SURVEY.md 8(e), strong scaling of
+    BASELINE config #5).  The initializers draw the full tensors and keep [lo, hi), so the union over the ranks is
+    exactly the single-GPU problem for the same seed; ``fscale`` stays 1/num_dims (the GLOBAL count) and the ranks'
+    partial f values are summed by the meta-step's all-reduce."""
     fscale = 1.0 / num_dims if normalize else 1.0
     two_pi = 6.2831855  # fp32(2 pi), the constant the kernel uses
+    lo, hi = shard if shard is not None else (0, num_dims)
+    n_loc = hi - lo
+
+    def sliced(init):
+        if shard is None:
+            return init
+        return lambda shape, gen: init((num_dims,), gen)[lo:hi].clone()
 
     def build():
-        x = get_variable("x", shape=[num_dims], initializer=random_normal_initializer(stddev=stddev))
-        b = get_variable("b", shape=[num_dims], initializer=random_normal_initializer(stddev=stddev), trainable=False)
-        c = get_variable("c", shape=[num_dims], initializer=random_normal_initializer(stddev=stddev), trainable=False)
+        normal = sliced(random_normal_initializer(stddev=stddev))
+        x = get_variable("x", shape=[n_loc], initializer=normal)
+        b = get_variable("b", shape=[n_loc], initializer=normal, trainable=False)
+        c = get_variable("c", shape=[n_loc], initializer=normal, trainable=False)
         fi = 0.5 * (x - b) ** 2 - alpha * c * torch.cos(two_pi * x) + alpha
         return fscale * torch.sum(fi)
     build.fused = FusedSpec("rastrigin_sep", "x", "b", "c", alpha=float(alpha), fscale=fscale)

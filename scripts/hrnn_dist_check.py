@@ -13,9 +13,16 @@ from open_l2o_b200.dist import shard_range  # noqa: E402
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
-    dist.init_process_group("nccl", device_id=dev)
+    # NCCL with one rank per GPU when the box has enough GPUs; otherwise all ranks run on cuda:0 and the collectives go
+    # through gloo (same kernels and sharding logic, different transport)
+    one_gpu_each = torch.cuda.device_count() >= world
+    local = int(os.environ["LOCAL_RANK"]) if one_gpu_each else 0
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if one_gpu_each:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
     shapes = [(300, 7), (5,), (1,), (64, 33)]          # includes tensors smaller than / not divisible by the world size
     K = 5
 
@@ -51,7 +58,8 @@ def main():
                 hid.append(rel(opt.get_slot(j, "log_learning_rate"), ref.get_slot(j, "log_learning_rate")[lo:hi]))
         errs["state_shard"] = max(hid)
         ok = all(v <= 1e-5 for v in errs.values())
-        print("hrnn sharded vs single-GPU:", errs, "PASS" if ok else "FAIL", flush=True)
+        print("hrnn sharded vs single-GPU (world %d, backend %s):" % (world, dist.get_backend()), errs,
+              "PASS" if ok else "FAIL", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

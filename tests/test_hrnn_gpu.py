@@ -59,12 +59,14 @@ def test_hrnn_steps_match_oracle(shapes, steps):
         for j, p in enumerate(params):
             n = p.numel()
             assert rel_err(gvars[j], p64[j]) <= slack, (t, j, "x")
-            assert rel_err(opt.update[off:off + n], u64[j]) <= 30 * slack, (t, j, "update")
+            e_u = rel_err(opt.update[off:off + n], u64[j])
+            assert e_u <= 3 * slack, (t, j, "update", e_u, slack)
             for key in ("parameter", "scl_decay", "inp_decay", "log_learning_rate", "grad_accum1", "grad_accum4",
                         "ms1", "ms4", "layer"):
-                assert rel_err(opt.get_slot(j, key), states64[j][key]) <= 10 * slack, (t, j, key)
+                e_k = rel_err(opt.get_slot(j, key), states64[j][key])
+                assert e_k <= 3 * slack, (t, j, key, e_k, slack)
             off += n
-        assert rel_err(opt.global_state, g64) <= 10 * slack, (t, "global")
+        assert rel_err(opt.global_state, g64) <= 3 * slack, (t, "global", rel_err(opt.global_state, g64), slack)
 
 
 def test_hrnn_argument_errors():
@@ -113,8 +115,7 @@ def test_hrnn_sharded_step_matches_single_gpu():
     import os
     import subprocess
     import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    # < 2 GPUs: both ranks share cuda:0 and the collectives go through gloo (see the script) - never skipped
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29541",

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import l2o_oracle as orc
-from tests.helpers import REL_TOL, rel_err
+from tests.helpers import REL_TOL, assert_theta_close, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -183,7 +183,7 @@ def test_training_trajectory_rastrigin_matches_oracle(fused, monkeypatch):
         res = tr.run_unroll(T)
         assert abs(cost - float(res.fx[-1])) <= 1e-5 * abs(float(res.fx[-1]))
         assert rel_err(xs[0], res.x_final) <= REL_TOL
-        assert rel_err(next(iter(prog.nets.values())).theta, tr.theta) <= 5e-5, it
+        assert_theta_close(next(iter(prog.nets.values())).theta, tr, it)
 
 
 def test_training_trajectory_quadratic_matches_oracle():
@@ -204,7 +204,7 @@ def test_training_trajectory_quadratic_matches_oracle():
         res = tr.run_unroll(20)
         assert abs(cost - float(res.fx[-1])) <= 1e-5 * abs(float(res.fx[-1])) + 1e-9
         assert rel_err(xs[0], res.x_final) <= REL_TOL
-        assert rel_err(next(iter(prog.nets.values())).theta, tr.theta) <= 5e-5, it
+        assert_theta_close(next(iter(prog.nets.values())).theta, tr, it)
 
 
 def test_rnnprop_training_matches_oracle():
@@ -241,7 +241,7 @@ def test_rnnprop_training_matches_oracle():
         res = tr.run_unroll(T)
         assert abs(cost - float(res.fx[-1])) <= 1e-5 * abs(float(res.fx[-1]))
         assert rel_err(np.concatenate([a.reshape(-1) for a in xs]), res.x_final) <= REL_TOL
-        assert rel_err(next(iter(prog.nets.values())).theta, tr.theta) <= 5e-5, it
+        assert_theta_close(next(iter(prog.nets.values())).theta, tr, it)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -283,7 +283,8 @@ def test_imitation_task_matches_oracle():
         cost = sess.run([loss_mt[0], update_mt[0], steps_mt[0]],
                         feed_dict={mt_inputs[0][0]: inputs.numpy(), mt_labels[0][0]: labels.numpy()})[0]
         assert abs(cost - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
-        assert rel_err(next(iter(prog.nets.values())).theta, theta) <= 5e-5, it
+        big = g.abs() > 1e-5 * float(g.abs().max())
+        assert rel_err(next(iter(prog.nets.values())).theta.cpu()[big], theta[big]) <= REL_TOL, it
 
 
 def test_scale_placeholders_random_scaling_trick():
@@ -354,4 +355,4 @@ def test_training_quadratic_fused_dense_groups():
         res = tr.run_unroll(T)
         assert abs(cost - float(res.fx[-1])) <= 1e-5 * abs(float(res.fx[-1])) + 1e-9
         assert rel_err(xs[0], res.x_final) <= REL_TOL
-        assert rel_err(next(iter(prog.nets.values())).theta, tr.theta) <= 5e-5, it
+        assert_theta_close(next(iter(prog.nets.values())).theta, tr, it)
