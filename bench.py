@@ -45,7 +45,10 @@ def parse():
     ap.add_argument("--engine", default="auto", choices=["auto", "ffma", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short runs of the other BASELINE configs (N=1 default run)")
-    ap.add_argument("--cpu-sample-coords", type=int, default=8192)
+    ap.add_argument("--cpu-sample-coords", type=int, default=0,
+                    help="coordinates of the CPU-oracle sample (0 = best of the workload's default sample sizes)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --coords per GPU (default 1M each); strong: --coords in TOTAL (default 1M) sharded over the ranks")
     return ap.parse_args()
 
 
@@ -60,16 +63,25 @@ WORKLOADS = {
             1004105, 20, "dm_logsign"),
     "rnnprop_mlp": ("L2O-RNNProp, MLP 784-100-10 synthetic batch 128, unroll=20 (BASELINE config #3)", 79510, 20,
                     "rnnprop"),
-    "quadratic": ("L2O-DM, quadratic 128x10, unroll=20 (BASELINE config #1; dense W_b x_b evaluated in-kernel)", 1280,
+    "quadratic": ("L2O-DM, quadratic 128x10, unroll=20 (BASELINE config #1; the reference's CPU-runnable case)", 1280,
                   20, "dm_identity"),
 }
+# Net output scale per workload.  The reference's synthetic-problem configs are {"layers": (20, 20)} => scale 1.0
+# (DM/util.py:136-143,231-246); with RANDOM-INIT weights (no trained .l2l exists offline) scale 1.0 drives x to
+# overflow within an unroll of 100, so the synthetic workloads run the same net at scale 0.1 ("final
+# Linear x0.1 so trajectories stay finite").  The arithmetic per coordinate-update does not depend on it.
+NET_SCALE = {"rastrigin": 0.1, "lasso": 0.1, "quadratic": 0.1, "mlp": 0.01, "rnnprop_mlp": 0.01}
+# step-at-a-time regime, SURVEY.md 8(d): state 640 + g 4 + x 8 (+ m, v 8 for RNNProp) per coordinate-update forward;
+# the BPTT sweep reads the checkpoint row (320) + the recorded gradient and net input (8) again
+STEP_BYTES = {"dm_identity": 652.0, "dm_logsign": 652.0, "rnnprop": 668.0}
+BWD_BYTES = {"dm_identity": 328.0, "dm_logsign": 328.0, "rnnprop": 336.0}
 
 
-def make_problem(name, coords, rank):
+def make_problem(name, coords, rank, shard=None):
     from open_l2o_b200 import problems
     if name == "rastrigin":
-        return problems.rastrigin_separable(num_dims=coords), {"cw": {"net": "CoordinateWiseDeepLSTM", "net_options": {
-            "layers": (20, 20), "scale": 0.1}}}, "dm"
+        return problems.rastrigin_separable(num_dims=coords, shard=shard), {"cw": {
+            "net": "CoordinateWiseDeepLSTM", "net_options": {"layers": (20, 20), "scale": 0.1}}}, "dm"
     if name == "quadratic":
         return problems.quadratic(batch_size=128, num_dims=10), {"cw": {"net": "CoordinateWiseDeepLSTM", "net_options": {
             "layers": (20, 20), "scale": 0.1}}}, "dm"
@@ -133,14 +145,78 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
-def quick_measure(workload, steps, warmup):
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def external_roofline(prog, netkind, T, t_unroll):
+    """HBM roofline of the step-at-a-time (external-gradient) regime, SURVEY.md 8(d): one `l2o_step` launch moves
+    652 B (668 B RNNProp) per coordinate; the BPTT sweep re-reads 328 B.  The step kernel and the BPTT kernel are timed
+    ALONE here with CUDA events on this workload's own buffers (inside the captured graph they cannot be bracketed)."""
+    from open_l2o_b200 import engine as eng
+    peaks = _peaks()
+    peak = float(peaks.get("hbm_gbs", 6500.0))
+    r = prog.runs[0]
+    h = r.net.handle
+    n = r.n
+    slot = max(h.state_floats * n, 1)
+    xw = prog.X.clone()
+    kw = {}
+    if h.n_in == 2:
+        kw = dict(m=r.m_work, v=r.v_work, beta1=prog.opt.beta1, beta2=prog.opt.beta2, step_ptr=prog.step_dev,
+                  t_offset=0, feat_out=r.feat_rec[0])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / reps
+    # walk the checkpoint slots so consecutive launches touch different state rows (no L2 reuse between launches)
+    idx = [0]
+
+    def step_once():
+        t = idx[0] % T
+        idx[0] += 1
+        h.step(r.net.theta, r.g_rec[t], r.ckpt[t * slot:(t + 1) * slot], r.ckpt[(t + 1) * slot:(t + 2) * slot],
+               x=xw[r.off:r.off + n], **kw)
+    t_step = timed(step_once, 2 * T)
+    dth = torch.zeros_like(prog.dtheta[r.key])
+    in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
+    t_bwd = timed(lambda: h.unroll_bwd(r.net.theta, n, T, in_seq, r.ckpt, dth, g_rec=r.g_rec), 3)
+    sb, bb = STEP_BYTES[netkind], BWD_BYTES[netkind]
+    ach = sb * n / t_step / 1e9
+    ws = (T + 1) * slot * 4
+    return {"bound": "hbm", "kernel": "l2o_step (one coordinate-wise LSTM step, state in HBM)", "achieved": ach,
+            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_bytes_per_coord_update": sb, "step_us": 1e6 * t_step, "coord_updates_per_s_step_kernel": n / t_step,
+            "bptt": {"kernel": "l2o_unroll_bwd over the T checkpoint slots", "ms": 1e3 * t_bwd,
+                     "algorithmic_bytes_per_coord_update": bb, "achieved": bb * n * T / t_bwd / 1e9,
+                     "frac": bb * n * T / t_bwd / 1e9 / peak, "coord_updates_per_s": n * T / t_bwd},
+            "train_unroll": {"algorithmic_bytes_per_coord_update": sb + bb,
+                             "achieved": (sb + bb) * n * T / t_unroll / 1e9,
+                             "frac": (sb + bb) * n * T / t_unroll / 1e9 / peak,
+                             "note": "whole unroll incl. the optimizee's own forward/backward (torch autograd) and Adam"},
+            "working_set_bytes": ws, "l2_resident": bool(ws < 126e6),
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s (B200_PROFILING.md)"}
+
+
+def quick_measure(workload, steps, warmup, with_cpu=True):
     """Short device-resident train-mode measurement of another BASELINE config through the same public surface
-    (MetaOptimizer.meta_minimize + Session.run([fx, update, step])); reported under "also" at N=1."""
+    (MetaOptimizer.meta_minimize + Session.run([fx, update, step])); reported under "also" at N=1 with its own
+    roofline and CPU baseline."""
     from open_l2o_b200 import engine as eng, meta
-    desc, coords, T, _ = WORKLOADS[workload]
+    desc, coords, T, netkind = WORKLOADS[workload]
     problem, net_config, flavour = make_problem(workload, coords, 0)
     cls = meta.RNNpropMetaOptimizer if flavour == "rnnprop" else meta.MetaOptimizer
-    optimizer = cls(seed=0, **net_config)
+    optimizer = cls(_seed=0, **net_config)
     _stdout = sys.stdout
     sys.stdout = open(os.devnull, "w")
     try:
@@ -162,11 +238,19 @@ def quick_measure(workload, steps, warmup):
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 1e3
+    launches = int(eng.launch_count() - l0)
     out = {"workload": desc, "coords": prog.N, "unroll": T, "mode": "train (fwd+BPTT+Adam)",
            "regime": "fused" if prog.fused is not None else "external-gradient (torch autograd between step kernels, "
            "one captured CUDA graph per unroll)", "value": prog.N * T * steps / t, "unit": "coordinate-updates/s",
            "ms_per_step": 1e3 * t / steps, "steps": steps, "warmup": warmup,
-           "gpu_launches": int(eng.launch_count() - l0), "last_fx": cost}
+           "gpu_launches": launches, "last_fx": cost, "net_scale": NET_SCALE[workload]}
+    out["roofline"] = external_roofline(prog, netkind, T, t / steps)
+    if with_cpu:
+        try:
+            out["cpu_baseline"] = cpu_baseline_for(workload, T, pick_cpu_threads(), timed=1)
+            out["vs_cpu_baseline"] = out["value"] / out["cpu_baseline"]["value"]
+        except Exception as ex:
+            out["cpu_baseline"] = {"error": repr(ex)[:200]}
     del sess, ms, prog, optimizer, problem
     torch.cuda.empty_cache()
     return out
@@ -261,36 +345,113 @@ def pick_cpu_threads():
     return max(1, min(os.cpu_count() or 1, 32))
 
 
-def cpu_oracle_rate(workload, T, coords, threads, mode="train"):
-    """Times the oracle (CPU restatement of the reference's algorithm) on a bounded sample of the workload."""
+CPU_SAMPLES = {"rastrigin": (8192, 32768), "mlp": (15910,), "lasso": (2000,), "rnnprop_mlp": (15910,), "quadratic": (1280,)}
+
+
+def cpu_oracle_unroll(workload, T, coords, threads, mode="train"):
+    """One unroll of the oracle (CPU restatement of the reference's algorithm, torch-CPU ops on all usable host
+    cores) on a bounded SAMPLE of `workload`: same net, same optimizee family, same T, `coords` coordinates instead of
+    the GPU arm's.  Returns (callable timing one unroll, coordinates of the sample, description)."""
     from oracle import l2o_oracle as orc   # bench.py's cpu_baseline / --impl reference leg only
     torch.set_num_threads(threads)
-    spec = orc.NetSpec(layers=(20, 20), scale=0.1)
-    theta = orc.init_theta(spec, seed=0, out_gain=1.0)
     gen = torch.Generator().manual_seed(1)
-    a, b, x0 = (torch.randn(coords, generator=gen) for _ in range(3))
-    prob = orc.FusedProblem("rastrigin_sep", a, b, 10.0, 1.0 / coords)
-    tr = orc.MetaTrainerOracle(spec, theta, None, lr=0.001, grad_of=prob.f_and_g)
-    tr.reset(x0)
+    grad_of, f = None, None
+    if workload == "rastrigin":
+        spec = orc.NetSpec(layers=(20, 20), scale=NET_SCALE[workload])
+        a, b, x0 = (torch.randn(coords, generator=gen) for _ in range(3))
+        grad_of = orc.FusedProblem("rastrigin_sep", a, b, 10.0, 1.0 / coords).f_and_g
+        what = "separable Rastrigin d=%d" % coords
+    elif workload == "quadratic":
+        spec = orc.NetSpec(layers=(20, 20), scale=NET_SCALE[workload])
+        B = max(1, coords // 10)
+        w, y = torch.rand(B, 10, 10, generator=gen), torch.rand(B, 10, generator=gen)
+        x0 = torch.randn(B, 10, generator=gen) * 0.01
+        f = lambda x: orc.quadratic_f(x, w, y)   # noqa: E731
+        what = "quadratic batch %d x 10" % B
+    elif workload == "lasso":
+        spec = orc.NetSpec(layers=(20, 20), scale=NET_SCALE[workload])
+        B = max(1, coords // 500)
+        A = torch.randn(B, 250, 500, generator=gen) / (250 ** 0.5)
+        bb = torch.randn(B, 250, 1, generator=gen)
+        x0 = torch.randn(B, 500, generator=gen) * 0.01
+        f = lambda x: orc.lasso_f(x, A, bb)      # noqa: E731
+        what = "Lasso m=250 n=500 batch %d (of the GPU arm's 128)" % B
+    elif workload in ("mlp", "rnnprop_mlp"):
+        if workload == "mlp":
+            spec = orc.NetSpec(layers=(20, 20), preprocess_name="LogAndSign", preprocess_options={"k": 5}, scale=0.01)
+        else:
+            spec = orc.NetSpec(layers=(20, 20), preprocess_name="fc", preprocess_options={"dim": 20}, scale=0.01,
+                               tanh_output=True, rnnprop=True)
+        hid = max(1, round((coords - 10) / 795.0))       # 784 h + h + 10 h + 10
+        data = torch.rand(128, 784, generator=gen)
+        labels = torch.randint(0, 10, (128,), generator=gen)
+        shapes = [(784, hid), (hid,), (hid, 10), (10,)]
+        n = sum(a * (b[0] if b else 1) for a, *b in shapes)
+        x0 = torch.randn(n, generator=gen) * 0.01
 
-    def one():
+        def f(xf):
+            off, ts = 0, []
+            for sh in shapes:
+                k = 1
+                for d in sh:
+                    k *= d
+                ts.append(xf[off:off + k].view(sh))
+                off += k
+            h = torch.sigmoid(data @ ts[0] + ts[1])
+            return torch.nn.functional.cross_entropy(h @ ts[2] + ts[3], labels)
+        what = "sigmoid MLP 784-%d-10, synthetic batch 128 (the GPU arm's optimizee at reduced width)" % hid
+    else:
+        raise ValueError(workload)
+    theta = orc.init_theta(spec, seed=0, out_gain=1.0)
+    tr = orc.MetaTrainerOracle(spec, theta, f, lr=0.001, grad_of=grad_of)
+    tr.reset(x0)
+    n = x0.numel()
+
+    def one(T_=T):
         t0 = time.perf_counter()
-        tr.run_unroll(T, train=(mode == "train"))
+        tr.run_unroll(T_, train=(mode == "train"))
         return time.perf_counter() - t0
-    return one
+    return one, n, what
+
+
+def cpu_baseline_for(workload, T, threads, sample_coords=0, timed=2):
+    """cpu_baseline object of one workload: best rate over the workload's sample sizes (torch's intra-op threading of
+    [N,80]-shaped tensors depends on N, so the sample size that suits the host is chosen by measurement)."""
+    best = None
+    sizes = (sample_coords,) if sample_coords else CPU_SAMPLES[workload]
+    for n_s in sizes:
+        one, n, what = cpu_oracle_unroll(workload, T, n_s, threads)
+        one(min(T, 5))                       # warm-up (allocator, thread pool) on a short unroll
+        ts = [one() for _ in range(timed)]
+        rate = n * T * len(ts) / sum(ts)
+        if best is None or rate > best["value"]:
+            best = {"value": rate, "unit": "coordinate-updates/s", "cores": threads, "kind": "port",
+                    "sample": "%d coordinates x T=%d train unroll (fwd + autograd BPTT + TF-Adam) of %s; torch-CPU oracle, "
+                              "%d timed unroll(s) after a short warm-up%s" % (
+                                  n, T, what, len(ts), "" if len(sizes) == 1 else "; best of samples %s" % (list(sizes),)),
+                    "sample_coords": n}
+    return best
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (TF-1.14/Sonnet cannot be installed
-    here; the oracle port stands in, kind="port")."""
+    """--impl reference: the reference's algorithm on the host cores (TF-1.14/Sonnet cannot be installed here,
+    DESIGN.md; the oracle port stands in, kind="port").  The line's `config` is what this arm actually ran: a bounded
+    SAMPLE of the workload (`cpu_sample: true`, `coords_per_gpu` = the sample's coordinates)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    desc, dcoords, dT, _ = WORKLOADS["rastrigin"]
+    desc, dcoords, dT, _ = WORKLOADS[args.workload]
     T = args.unroll or dT
     threads = pick_cpu_threads()
-    n = args.cpu_sample_coords
-    one = cpu_oracle_rate("rastrigin", T, n, threads)
+    sizes = (args.cpu_sample_coords,) if args.cpu_sample_coords else CPU_SAMPLES[args.workload]
+    best = None
+    for n_s in sizes:                        # probe: one short + one full unroll per candidate sample size
+        one, n, what = cpu_oracle_unroll(args.workload, T, n_s, threads)
+        one(min(T, 5))
+        rate = n * T / one()
+        if best is None or rate > best[0]:
+            best = (rate, one, n, what)
+    _, one, n, what = best
     for _ in range(args.warmup):
         one()
     times = [one() for _ in range(args.steps)]
@@ -299,10 +460,13 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "coordinate-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "coords_per_gpu": dcoords, "unroll": T, "mode": "train (fwd+BPTT+Adam)"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "coords_per_gpu": n, "cpu_sample": True,
+                   "gpu_arm_coords": args.coords or dcoords, "unroll": T, "mode": "train (fwd+BPTT+Adam)",
+                   "net_scale": NET_SCALE[args.workload], "sample_sizes_probed": list(sizes)},
         "cpu_baseline": {"value": value, "unit": "coordinate-updates/s", "cores": threads, "kind": "port",
-                         "sample": "%d coordinates x T=%d train unroll per step (torch-CPU oracle, autograd BPTT)" % (n, T)},
+                         "sample": "%d coordinates x T=%d train unroll per step of %s (torch-CPU oracle, autograd BPTT); "
+                                   "a bounded sample of the GPU arm's workload, not its full size" % (n, T, what)},
         "e2e": {"value": value, "unit": "coordinate-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -343,9 +507,21 @@ def main():
     desc, dcoords, dT, netkind = WORKLOADS[args.workload]
     coords = args.coords or dcoords
     T = args.unroll or dT
-    problem, net_config, flavour = make_problem(args.workload, coords, rank)
+    strong = args.scaling == "strong"
+    if strong:
+        # BASELINE config #5 as written: ONE 1M-coordinate problem, coordinates sharded over the ranks
+        if args.workload != "rastrigin":
+            raise SystemExit("--scaling strong is defined for the coordinate-sharded rastrigin workload")
+        from open_l2o_b200.dist import shard_range
+        total_coords = coords
+        problem, net_config, flavour = make_problem(args.workload, total_coords, rank,
+                                                    shard=shard_range(total_coords, rank, world))
+        seed = 0           # every rank draws the same global tensors and keeps its slice
+    else:
+        problem, net_config, flavour = make_problem(args.workload, coords, rank)
+        seed = rank
     cls = meta.RNNpropMetaOptimizer if flavour == "rnnprop" else meta.MetaOptimizer
-    optimizer = cls(seed=rank, distributed=distributed, **net_config)
+    optimizer = cls(_seed=seed, _distributed=distributed, **net_config)
     _stdout = sys.stdout
     sys.stdout = open(os.devnull, "w")      # the reference prints variable lists at graph build; keep stdout = 1 JSON line
     try:
@@ -388,7 +564,19 @@ def main():
     if distributed:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev = float(tt.item())
-    value = coords * world * T * args.steps / t_dev
+    job_coords = total_coords if strong else coords * world      # coordinates the WHOLE job updates per step
+    value = job_coords * T * args.steps / t_dev
+
+    # ---- N>1 consistency: after the all-reduced meta-steps every rank must hold the identical theta ----------------
+    theta_check = None
+    if distributed:
+        th = next(iter(prog.nets.values())).theta
+        ck = torch.stack([th.double().sum(), th.double().abs().sum()])
+        allck = [torch.zeros_like(ck) for _ in range(world)]
+        dist.all_gather(allck, ck)
+        theta_check = {"rank0_sum": float(allck[0][0]), "identical_on_all_ranks": bool(all(torch.equal(allck[0], c) for c in allck))}
+        if not theta_check["identical_on_all_ranks"]:
+            raise SystemExit("theta diverged across ranks: %r" % ([c.tolist() for c in allck],))
 
     # ---- per-kernel timing of the dominant kernel (BPTT) for the roofline ---------------------------
     kb0, kb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -441,9 +629,19 @@ def main():
                                "ms": 1e3 * t_f, "coord_updates_per_s": r.n * T / t_f},
                 "bwd_ms": 1e3 * t_b, "bwd_coord_updates_per_s": r.n * T / t_b,
                 "alg_flop_per_coord_update": {"fwd": fl, "bwd": 2 * fl},
+                "algorithmic_bytes_8d_fused": 8.0 * r.n * T,
+                "traffic_over_8d_fused": (traffic / (8.0 * r.n * T)) if traffic else None,
+                "traffic_note": "SURVEY.md 8(d) puts the fused regime at 4-8 B per coordinate-update (inference: g in, "
+                                "x out).  TRAINING by recompute must also write (forward) and read (BPTT) the "
+                                "checkpoint row: 320 B + g 4 B + net input 4 B = 328 B per coordinate-update per "
+                                "direction = `algorithmic_bytes`; the measured DRAM traffic is ~41x the 8 B figure and "
+                                "1.01x the checkpoint figure",
                 "notes": "fp32 parity => 3xTF32 (tf32 = 1/2 bf16 rate): a 100%-busy tensor pipe reads 1/6 of this peak "
                          "(ncu: tensor pipe 30% active in this kernel, 22% in the forward kernel); the activation pipe "
                          "(320 MUFU ops per coordinate-update forward, 400 backward) caps the path near 1.4e10 upd/s/GPU"}
+
+    if roof is None:      # external-gradient workloads: HBM roofline of the step kernel (+ BPTT) on this workload
+        roof = external_roofline(prog, netkind, T, t_dev / args.steps)
 
     # ---- infer mode (evaluate_dm.py: forward unroll only, no checkpoints) -----------------------------
     infer = None
@@ -463,49 +661,39 @@ def main():
         ti = torch.tensor([t_i], dtype=torch.float64, device=dev)
         if distributed:
             dist.all_reduce(ti, op=dist.ReduceOp.MAX)
-        infer = {"value": coords * world * T / float(ti.item()), "unit": "coordinate-updates/s", "ms_per_unroll": 1e3 * t_i,
+        infer = {"value": job_coords * T / float(ti.item()), "unit": "coordinate-updates/s", "ms_per_unroll": 1e3 * t_i,
                  "mode": "infer (forward unroll only, state on-chip, no checkpoint writes; l2o_unroll_fwd)"}
 
     # ---- end-to-end through the public API with HOST buffers ------------------------------------
-    e2e = None
-    if prog.fused is not None:
-        f = prog.fused
-        hx = prog.X.cpu().pin_memory()
-        ha = prog.const_vals[f.a].cpu().pin_memory()
-        hb = prog.const_vals[f.b].cpu().pin_memory()
-        hout = torch.empty(coords, dtype=torch.float32).pin_memory()
-        fetch2 = [ms.fx, ms.update, ms.step]
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
-            prog.X.copy_(hx, non_blocking=True)
-            prog.const_vals[f.a].copy_(ha, non_blocking=True)
-            prog.const_vals[f.b].copy_(hb, non_blocking=True)
-            cost = sess.run(fetch2)[0]                 # float(fx) = device->host read of the loss
-            hout.copy_(prog.X, non_blocking=True)      # updated parameters back to the host
-        g1.record()
-        barrier()
-        t_e = torch.tensor([g0.elapsed_time(g1) / 1e3], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": coords * world * T * args.steps / float(t_e.item()), "unit": "coordinate-updates/s",
-               "h2d_bytes_per_step": 4 * (hx.numel() + ha.numel() + hb.numel()), "d2h_bytes_per_step": 4 * coords + 8}
-    else:
-        e2e = {"value": value, "unit": "coordinate-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
-               "note": "external-gradient workload: optimizee tensors are device-resident by construction"}
+    # every step: the optimizee's parameters AND problem constants come from pinned host memory (H2D inside the timed
+    # region, written in place so captured graphs stay valid), one meta-step through Session.run, the loss is read
+    # back by float(fx) and the updated parameters are copied to the host
+    hx = prog.X.cpu().pin_memory()
+    hconst = {k: v.cpu().pin_memory() for k, v in prog.const_vals.items()}
+    hout = torch.empty(coords, dtype=torch.float32).pin_memory()
+    fetch2 = [ms.fx, ms.update, ms.step]
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        prog.X.copy_(hx, non_blocking=True)
+        for k, hv in hconst.items():
+            prog.const_vals[k].copy_(hv, non_blocking=True)
+        cost = sess.run(fetch2)[0]                 # float(fx) = device->host read of the loss
+        hout.copy_(prog.X, non_blocking=True)      # updated parameters back to the host
+    g1.record()
+    barrier()
+    t_e = torch.tensor([g0.elapsed_time(g1) / 1e3], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e = {"value": job_coords * T * args.steps / float(t_e.item()), "unit": "coordinate-updates/s",
+           "h2d_bytes_per_step": 4 * (hx.numel() + sum(v.numel() for v in hconst.values())),
+           "d2h_bytes_per_step": 4 * coords + 8, "bytes_are": "per rank"}
 
     # ---- CPU baseline (oracle port on the host cores; rank 0, N=1 only) ----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = pick_cpu_threads()
-        n_s = args.cpu_sample_coords
-        one = cpu_oracle_rate(args.workload, T, n_s, threads)
-        one()
-        ts = [one() for _ in range(2)]
-        cpu = {"value": n_s * T * len(ts) / sum(ts), "unit": "coordinate-updates/s", "cores": threads, "kind": "port",
-               "sample": "%d coordinates x T=%d separable-Rastrigin train unroll (fwd+autograd BPTT+Adam), torch-CPU "
-                         "oracle, %d timed unrolls after 1 warm-up" % (n_s, T, len(ts))}
+        cpu = cpu_baseline_for(args.workload, T, pick_cpu_threads(), args.cpu_sample_coords)
 
     also = None
     if rank == 0 and world == 1 and args.workload == "rastrigin" and not args.no_also:
@@ -524,10 +712,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "coordinate-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "coords_per_gpu": coords, "unroll": T, "mode": "train (fwd+BPTT+Adam)",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc if not strong else desc.replace("d=1e6 per GPU", "d=%d in total" % total_coords),
+                       "coords_per_gpu": coords, "coords_total": job_coords, "unroll": T,
+                       "mode": "train (fwd+BPTT+Adam)",
                        "regime": "fused" if prog.fused is not None else "external-gradient",
                        "engine": args.engine, "parallelism": "dp%d (coordinates sharded)" % world,
+                       "net_scale": NET_SCALE[args.workload], "theta_check": theta_check,
                        "l2_policy": "working set (checkpoints %.1f GB/GPU) >> 126 MB L2" % (r.ckpt.numel() * 4 / 1e9),
                        "last_fx": cost},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,

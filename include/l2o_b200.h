@@ -17,6 +17,7 @@
  *   l2o_unroll_bwd                      tf.gradients(loss, theta) through that loop    DM/meta.py:412 (BPTT)
  *   l2o_adam_step                       tf.train.AdamOptimizer(lr).minimize            DM/meta.py:411-413
  *   l2o_log_and_sign                    preprocess.LogAndSign                          DM/preprocess.py:52-70
+ *   l2o_lasso_grad                      problems.lasso(_fixed) loss + tf.gradients     DM/problems.py:103-175, DM/meta.py:322-329
  *
  * Conventions: every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); no hidden
  * allocation; `stream` is a cudaStream_t passed as void*; every entry returns 0 or a negative
@@ -156,6 +157,25 @@ int l2o_adam_step(float* theta, const double* dtheta, float* m, float* v, int64_
 
 /* out [2][n]: row 0 = max(log(|g|+eps)/k, -1), row 1 = clip(g*e^k, -1, 1). */
 int l2o_log_and_sign(const float* g, float* out, int64_t n, float k, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused gradient producers: f and df/dx of a synthetic optimizee family in ONE launch, replacing
+ * the ~15 TF ops + tf.gradients of the reference's graph (DM/problems.py:103-175, DM/meta.py:322-329).
+ *
+ *   l2o_lasso_grad   problems.lasso / lasso_fixed:  f = mean_b(0.5 ||A_b x_b - y_b||^2 + l1 ||x_b||_1)
+ *                    g = dF/dx;  with `scale` (random-scaling trick, DM/meta_dm_train.py:336-338,384-385) the loss is
+ *                    evaluated at x (.) scale and g is multiplied by scale. */
+typedef struct {
+  int32_t batch, m, n;  /* A [batch][m][n], y [batch][m], x [batch][n] (row-major) */
+  const float* A;
+  const float* y;
+  const float* x;
+  const float* scale;   /* optional [batch][n] */
+  float l1;
+  float* g;             /* [batch][n] */
+  double* f;            /* optional scalar: += f */
+} l2o_lasso_args;
+int l2o_lasso_grad(const l2o_lasso_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * L2O-Scale HierarchicalRNN update step (BASELINE config #4).

@@ -24,7 +24,7 @@ ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
 # every symbol include/l2o_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "l2o_net_create", "l2o_net_destroy", "l2o_net_set_engine", "l2o_theta_count", "l2o_state_floats", "l2o_workspace_bytes",
-    "l2o_step", "l2o_unroll_fwd", "l2o_unroll_bwd", "l2o_adam_step", "l2o_log_and_sign",
+    "l2o_step", "l2o_unroll_fwd", "l2o_unroll_bwd", "l2o_adam_step", "l2o_log_and_sign", "l2o_lasso_grad",
     "l2o_launch_count", "l2o_status_string", "l2o_last_cuda_error", "l2o_version",
     "l2o_hrnn_create", "l2o_hrnn_destroy", "l2o_hrnn_theta_count", "l2o_hrnn_state_floats", "l2o_hrnn_coords",
     "l2o_hrnn_workspace_bytes", "l2o_hrnn_init_state", "l2o_hrnn_prepare", "l2o_hrnn_step",
@@ -59,6 +59,11 @@ class UnrollArgs(C.Structure):
 class BwdArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("theta", _fp), ("in_seq", _fp), ("ckpt", _fp), ("g_rec", _fp),
                 ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp), ("delta_seq", _fp)]
+
+
+class LassoArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("m", C.c_int32), ("n", C.c_int32), ("A", _fp), ("y", _fp), ("x", _fp),
+                ("scale", _fp), ("l1", C.c_float), ("g", _fp), ("f", _fp)]
 
 
 class HrnnArgs(C.Structure):
@@ -156,6 +161,8 @@ def lib():
     L.l2o_adam_step.restype = C.c_int
     L.l2o_log_and_sign.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]
     L.l2o_log_and_sign.restype = C.c_int
+    L.l2o_lasso_grad.argtypes = [C.POINTER(LassoArgs), C.c_void_p]
+    L.l2o_lasso_grad.restype = C.c_int
     L.l2o_launch_count.argtypes = []
     L.l2o_launch_count.restype = C.c_int64
     L.l2o_hrnn_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32]

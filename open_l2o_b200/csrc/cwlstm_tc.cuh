@@ -414,15 +414,25 @@ struct Smem {
   uint64_t wbar;
   uint64_t a_ready[kTiles];
   uint64_t d_ready[kTiles];
+  uint64_t full[2], empty[2];     // STAGE: state rows of a tile pair landed in / drained from staging buffer b
   uint32_t tmem_slot;
   uint32_t pad;
   double fx[1];                   // [T+1], dynamic tail
 };
+// STAGE (l2o_step, T = 1): the (h, c) rows of the NEXT tile pair are pulled into shared memory by TMA bulk copies while
+// the current pair computes, so the HBM read of the 320 B/coordinate state overlaps the epilogue instead of preceding
+// it.  Two buffers x kTiles tiles x 4 arrays (h1, c1, h2, c2) x [128][kH] floats = 160 KB after the fx tail.
+constexpr int kStageArr = 128 * kH;                       // floats per (tile, array)
+constexpr int kStageFloats = 2 * kTiles * 4 * kStageArr;  // 40960 floats
+__host__ __device__ constexpr size_t stage_offset(int T) {
+  return (sizeof(Smem) + (size_t)(T + 1) * sizeof(double) + 127) & ~(size_t)127;
+}
 
 // Epilogue of one thread: coordinate `row` of tile `tile`, hidden units [U0, U0+NU) of both layers.
-template <class C, int HALF>
+template <class C, int HALF, bool STAGE>
 __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const NetRt& rt, Smem& S, uint32_t tmem_base,
-                                             float* __restrict__ state_out, int warp, int lane) {
+                                             float* __restrict__ state_out, int warp, int lane,
+                                             const float* __restrict__ stage) {
   constexpr int U0 = HalfUnits<HALF>::U0;
   constexpr int NU = HalfUnits<HALF>::NU;
   const int tile = warp >> 3;          // warps 0-7: tile 0, 8-15: tile 1
@@ -444,10 +454,12 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
     tmem_st4(t_ah + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
     tmem_st4(t_al + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
   }
-  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+  uint32_t pfull[2] = {0, 0};
+  int kpair = 0;
+  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++kpair) {
     const int64_t i = pair * kTileCoords + tile * 128 + row;
     const bool act = i < n;
-    {  // pull the NEXT pair's state rows towards L2: with T = 1 (l2o_step) the loads below are the critical path
+    if constexpr (!STAGE) {  // pull the NEXT pair's state rows towards L2: with T = 1 the loads below are the critical path
       const int64_t inx = i + (int64_t)gridDim.x * kTileCoords;
       if (inx < n) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state + inx * kH + U0));
@@ -466,11 +478,26 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       float h1[NU], h2[NU];
 #pragma unroll
       for (int k = 0; k < NU; ++k) { h1[k] = 0.f; h2[k] = 0.f; c1[k] = 0.f; c2[k] = 0.f; }
+      if constexpr (STAGE) {
+        const int buf = kpair & 1;
+        mbar_wait(&S.full[buf], pfull[buf]);
+        pfull[buf] ^= 1;
+        if (act) {
+          const float* sb = stage + (size_t)((buf * kTiles + tile) * 4) * kStageArr + row * kH + U0;
+          load_units<HALF>(sb, h1);
+          load_units<HALF>(sb + kStageArr, c1);
+          load_units<HALF>(sb + 2 * kStageArr, h2);
+          load_units<HALF>(sb + 3 * kStageArr, c2);
+        }
+        mbar_arrive(&S.empty[buf]);   // release: the producer may refill this buffer (two pairs ahead)
+      }
       if (act) {
-        load_units<HALF>(a.state + i * kH + U0, h1);
-        load_units<HALF>(a.state + (n + i) * kH + U0, c1);
-        load_units<HALF>(a.state + 2 * n * kH + i * kH + U0, h2);
-        load_units<HALF>(a.state + 2 * n * kH + (n + i) * kH + U0, c2);
+        if constexpr (!STAGE) {
+          load_units<HALF>(a.state + i * kH + U0, h1);
+          load_units<HALF>(a.state + (n + i) * kH + U0, c1);
+          load_units<HALF>(a.state + 2 * n * kH + i * kH + U0, h2);
+          load_units<HALF>(a.state + 2 * n * kH + (n + i) * kH + U0, c2);
+        }
         if (a.ckpt) {
           store_units<HALF>(a.ckpt + i * kH + U0, h1);
           store_units<HALF>(a.ckpt + (n + i) * kH + U0, c1);
@@ -606,7 +633,7 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
   }
 }
 
-template <class C>
+template <class C, bool STAGE>
 __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args a, NetRt rt, const float* __restrict__ img,
                                                                   float* __restrict__ state_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -630,6 +657,10 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
         mbar_init(&S.a_ready[k], 256);
         mbar_init(&S.d_ready[k], 1);
       }
+      mbar_init(&S.full[0], 1);
+      mbar_init(&S.full[1], 1);
+      mbar_init(&S.empty[0], kEpiThreads);
+      mbar_init(&S.empty[1], kEpiThreads);
       fence_barrier_init();
     }
     __syncwarp();
@@ -648,10 +679,48 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
   if (warp < kIssuerWarp) {
     // =============================== epilogue warps: a thread pair per coordinate ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFwdEpiRegs));
-    if (((warp >> 2) & 1) == 0) fwd_epilogue<C, 0>(a, rt, S, tmem_base, state_out, warp, lane);
-    else fwd_epilogue<C, 1>(a, rt, S, tmem_base, state_out, warp, lane);
+    const float* stage = reinterpret_cast<const float*>(smem_raw + stage_offset(T));
+    if (((warp >> 2) & 1) == 0) fwd_epilogue<C, 0, STAGE>(a, rt, S, tmem_base, state_out, warp, lane, stage);
+    else fwd_epilogue<C, 1, STAGE>(a, rt, S, tmem_base, state_out, warp, lane, stage);
   } else if (warp > kIssuerWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFwdIssuerRegs));  // idle warps of the issuer warpgroup
+    if constexpr (STAGE) {
+      if (warp == kIssuerWarp + 1) {
+        // ---- state-row producer: TMA bulk copies of pair k+0, k+1 ... into the two staging buffers -------------------
+        float* stage = reinterpret_cast<float*>(smem_raw + stage_offset(T));
+        uint32_t pempty[2] = {0, 0};
+        int k = 0;
+        for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++k) {
+          const int buf = k & 1;
+          if (k >= 2) {
+            mbar_wait(&S.empty[buf], pempty[buf]);
+            pempty[buf] ^= 1;
+          }
+          if (lane == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int tile = 0; tile < kTiles; ++tile) {
+              const int64_t base = pair * kTileCoords + tile * 128;
+              const int64_t cnt = n - base < 0 ? 0 : (n - base > 128 ? 128 : n - base);
+              total += (uint32_t)cnt * 4u * kH * 4u;
+            }
+            mbar_expect_tx(&S.full[buf], total);
+#pragma unroll
+            for (int tile = 0; tile < kTiles; ++tile) {
+              const int64_t base = pair * kTileCoords + tile * 128;
+              const int64_t cnt = n - base < 0 ? 0 : (n - base > 128 ? 128 : n - base);
+              if (cnt > 0) {
+#pragma unroll
+                for (int arr = 0; arr < 4; ++arr)
+                  tma_bulk_g2s(stage + (size_t)((buf * kTiles + tile) * 4 + arr) * kStageArr,
+                               a.state + (int64_t)arr * n * kH + base * kH, (uint32_t)cnt * kH * 4u, &S.full[buf]);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else {
     // =============================== MMA issuer warp ===============================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFwdIssuerRegs));
@@ -715,11 +784,14 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
 
 // ------------------------------------------------------------------ host side (called from l2o_capi.cu)
 template <class C>
-int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms, float* state_out = nullptr) {
+int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms, float* state_out = nullptr,
+                  bool stage = false) {
   tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 0);
-  auto k = tc::unroll_fwd_kernel<C>;
-  const size_t smem = sizeof(tc::Smem) + (size_t)(a.T + 1) * sizeof(double) + 128;
-  if (smem > 220 * 1024) return L2O_E_INVALID;
+  // stage: TMA-prefetched state rows (the l2o_step path, T = 1); needs 16-byte aligned arrays (n * 80 B always is)
+  stage = stage && (reinterpret_cast<uintptr_t>(a.state) % 16 == 0);
+  auto k = stage ? tc::unroll_fwd_kernel<C, true> : tc::unroll_fwd_kernel<C, false>;
+  const size_t smem = tc::stage_offset(a.T) + (stage ? (size_t)tc::kStageFloats * sizeof(float) : 0) + 128;
+  if (smem > 227 * 1024) return L2O_E_INVALID;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
   const int64_t npairs = (a.n + tc::kTileCoords - 1) / tc::kTileCoords;
   const int grid = (int)(npairs < sms ? npairs : sms);

@@ -2,6 +2,8 @@
 #include "cwlstm_ffma.cuh"   // load_vec / store_vec / preprocess helpers
 #include "cwlstm_tc.cuh"
 #include "cwlstm_tc_bwd.cuh"
+#include "cwlstm_tc_bwd2.cuh"
+#include <cstdlib>
 #include "l2o_internal.h"
 
 namespace l2o {
@@ -37,8 +39,16 @@ int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {
   const int sms = device_sms();
   if (sms <= 0) return L2O_E_CUDA;
   rc = L2O_E_UNSUPPORTED;
-  if (h->cfg == 0) rc = tc_launch_bwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms);
-  if (h->cfg == 1) rc = tc_launch_bwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+  // L2O_BWD_V1=1 selects the first-generation (phase-serial) kernel for A/B measurements; the layer-pipelined kernel
+  // (cwlstm_tc_bwd2.cuh) is the product path
+  static const bool v1 = std::getenv("L2O_BWD_V1") != nullptr && std::getenv("L2O_BWD_V1")[0] == '1';
+  if (v1) {
+    if (h->cfg == 0) rc = tc_launch_bwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+    if (h->cfg == 1) rc = tc_launch_bwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+  } else {
+    if (h->cfg == 0) rc = tc_launch_bwd2<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+    if (h->cfg == 1) rc = tc_launch_bwd2<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+  }
   if (rc == L2O_OK) count_launch(2);
   if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_unroll_bwd launch");
   return rc;
@@ -66,8 +76,10 @@ int tc_step(l2o_net* h, const l2o_step_args& s, cudaStream_t st) {
   a.state = const_cast<float*>(s.state_in);
   a.delta_seq = s.delta;
   rc = L2O_E_UNSUPPORTED;
-  if (h->cfg == 0) rc = tc_launch_fwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out);
-  if (h->cfg == 1) rc = tc_launch_fwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out);
+  // L2O_STEP_STAGE=0 disables the TMA-staged state loads (A/B measurements)
+  static const bool stage = !(std::getenv("L2O_STEP_STAGE") != nullptr && std::getenv("L2O_STEP_STAGE")[0] == '0');
+  if (h->cfg == 0) rc = tc_launch_fwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage);
+  if (h->cfg == 1) rc = tc_launch_fwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage);
   if (rc == L2O_OK) count_launch(2);
   if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_step launch");
   return rc;

@@ -159,6 +159,21 @@ def log_and_sign(g: torch.Tensor, k: float) -> torch.Tensor:
     return out
 
 
+def lasso_grad(A, y, x, l1, g, f=None, scale=None):
+    """f and df/dx of problems.lasso / lasso_fixed in one launch (DM/problems.py:103-175): A [B,m,n], y [B,m(,1)],
+    x [B*n] flat; writes g [B*n] and accumulates the scalar loss into the fp64 tensor ``f`` (if given)."""
+    a = _lib.LassoArgs()
+    a.batch, a.m, a.n = int(A.shape[0]), int(A.shape[1]), int(A.shape[2])
+    if x.numel() != a.batch * a.n or g.numel() != a.batch * a.n or y.numel() != a.batch * a.m:
+        raise L2OError("lasso_grad: shape mismatch")
+    a.A, a.y, a.x = _ptr(A, name="A"), _ptr(y, name="y"), _ptr(x, name="x")
+    a.scale = _ptr(scale, name="scale")
+    a.l1 = float(l1)
+    a.g = _ptr(g, name="g")
+    a.f = _ptr(f, torch.float64, "f")
+    _lib.check(_lib.lib().l2o_lasso_grad(C.byref(a), _stream()), "l2o_lasso_grad")
+
+
 _graph_replayed = 0  # kernels of this library launched through CUDA-graph replays (not visible to the C-side counter)
 
 

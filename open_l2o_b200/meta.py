@@ -26,6 +26,7 @@ from . import engine as _engine
 from . import networks
 from .variables import variable_getter
 
+_PRODUCER_KINDS = ("lasso_batch",)
 MetaLoss = collections.namedtuple("MetaLoss", "loss, update, reset, fx, x")
 MetaStep = collections.namedtuple("MetaStep", "step, update, reset, fx, x")
 
@@ -181,6 +182,12 @@ class _Program(object):
         self.fused = getattr(make_loss, "fused", None) if os.environ.get("L2O_DISABLE_FUSED") != "1" else None
         if self.fused is not None and not (len(self.runs) == 1 and len(self.variables) == 1 and self.runs[0].n == self.N):
             self.fused = None
+        # "producer" optimizees: f and df/dx come from ONE library kernel per step instead of
+        # torch autograd (~15 launches); the unroll stays step-at-a-time (the gradient couples coordinates) and is
+        # captured into one CUDA graph like every external-gradient unroll
+        self.producer = None
+        if self.fused is not None and self.fused.kind in _PRODUCER_KINDS:
+            self.producer, self.fused = self.fused, None
         self.adam = {k: dict(m=torch.zeros_like(net.theta), v=torch.zeros_like(net.theta), k=0)
                      for k, net in self.nets.items()}
         self.dtheta = {k: torch.zeros(net.theta.numel(), dtype=torch.float64, device=self.device)
@@ -291,9 +298,23 @@ class _Program(object):
         return [self.X[self.var_off[j]:self.var_off[j] + (int(np.prod(v["shape"])) if v["shape"] else 1)]
                 .reshape(v["shape"]).cpu().numpy() for j, v in enumerate(self.variables)]
 
+    def _produce(self, Xflat):
+        """f(x) and df/dx from the fused producer kernel (one launch)."""
+        p = self.producer
+        g = torch.empty_like(Xflat)
+        fx = torch.zeros((), dtype=torch.float64, device=self.device)
+        if p.kind == "lasso_batch":
+            _engine.lasso_grad(self.const_vals[p.a], self.const_vals[p.b], Xflat, p.alpha, g, f=fx,
+                               scale=self.scale_flat if self.scale_active else None)
+        else:
+            raise ValueError(p.kind)
+        return fx, g
+
     def _value_and_grad(self, Xflat):
         """f(x) and df/dx as a flat [N] tensor.  Each variable is its own autograd leaf (a view of the arena), so the
         backward pass produces one gradient per variable and never materialises zero-filled [N] tensors."""
+        if self.producer is not None:
+            return self._produce(Xflat)
         leaves = [v.detach().requires_grad_(True) for v in self._var_views(Xflat)]
         with torch.enable_grad():
             fx = self._loss_from_vars(leaves)
@@ -361,8 +382,11 @@ class _Program(object):
             for r in self.runs:
                 r.g_rec[T].copy_(g[r.off:r.off + r.n])
         else:
-            with torch.no_grad():
-                fx = self._loss_at(Xw)
+            if self.producer is not None:
+                fx = self._produce(Xw)[0]
+            else:
+                with torch.no_grad():
+                    fx = self._loss_at(Xw)
         fxs.append(fx)
         for r in self.runs:
             slot = max(r.net.handle.state_floats * r.n, 1)

@@ -16,7 +16,8 @@ from .variables import (constant_initializer, get_variable, ones_initializer, ra
 
 @dataclass
 class FusedSpec:
-    kind: str        # "rastrigin_sep" | "quadratic_diag" | "quadratic_batch"  (include/l2o_b200.h L2O_OPT_*)
+    kind: str        # "rastrigin_sep" | "quadratic_diag" | "quadratic_batch" (in-kernel, include/l2o_b200.h L2O_OPT_*)
+                     # | "lasso_batch" (producer kernel l2o_lasso_grad: a = A / w, b = y, alpha = l1 weight)
     var: str         # name of the trainable variable
     a: str           # constant names
     b: str
@@ -75,6 +76,7 @@ def lasso(batch_size=128, num_dims=10, stddev=0.01, l=0.005):
         y = get_variable("y", shape=[batch_size, num_dims, 1], initializer=random_uniform_initializer(),
                          trainable=False)
         return _lasso_loss(x, w, y, l)
+    build.fused = FusedSpec("lasso_batch", "x", "w", "y", alpha=float(l))   # producer kernel: f and df/dx in one launch
     return build
 
 
@@ -88,6 +90,7 @@ def lasso_fixed(data_A, data_b, stddev=0.01, l=0.005):
         w = get_variable("w", shape=list(a.shape), initializer=constant_initializer(a), trainable=False)
         y = get_variable("y", shape=list(b.shape), initializer=constant_initializer(b), trainable=False)
         return _lasso_loss(x, w, y, l)
+    build.fused = FusedSpec("lasso_batch", "x", "w", "y", alpha=float(l))   # producer kernel: f and df/dx in one launch
     return build
 
 

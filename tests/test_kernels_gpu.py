@@ -335,3 +335,27 @@ def test_unroll_fused_quadratic_batch(B, d):
     with pytest.raises(Exception):   # a group must not straddle the problem
         h.unroll_fwd(th, n, T, arena, opt_kind=OPT_KINDS["quadratic_batch"], opt_a=w.reshape(-1).to(DEV),
                      opt_b=y.reshape(-1).to(DEV), opt_fscale=1.0 / B, opt_group=d + 1 if n % (d + 1) else 0, x=x)
+
+
+@pytest.mark.parametrize("B,m,n", [(3, 7, 13), (2, 250, 500), (5, 64, 33), (1, 1, 1)])
+@pytest.mark.parametrize("scaled", [False, True])
+def test_lasso_grad_producer(B, m, n, scaled):
+    """l2o_lasso_grad (f and df/dx of DM/problems.py:103-175 in one launch) vs torch autograd of the oracle's loss in
+    fp64, incl. exact zeros in x (sign(0) = 0) and the random-scaling chain rule (DM/meta_dm_train.py:384-385)."""
+    from open_l2o_b200 import engine
+    gen = torch.Generator().manual_seed(17)
+    A = torch.randn(B, m, n, generator=gen) / (m ** 0.5)
+    y = torch.randn(B, m, 1, generator=gen)
+    x = torch.randn(B, n, generator=gen) * 0.3
+    x.view(-1)[::5] = 0.0
+    sc = torch.exp(torch.rand(B, n, generator=gen) * 6 - 3) if scaled else None
+    xd = x.double().requires_grad_(True)
+    f_ref = orc.lasso_f(xd * sc.double() if scaled else xd, A.double(), y.double(), 0.005)
+    (g_ref,) = torch.autograd.grad(f_ref, xd)
+    g = torch.empty(B * n, device=DEV)
+    f = torch.zeros((), dtype=torch.float64, device=DEV)
+    engine.lasso_grad(A.to(DEV), y.to(DEV), x.reshape(-1).to(DEV), 0.005, g, f=f,
+                      scale=sc.reshape(-1).to(DEV) if scaled else None)
+    torch.cuda.synchronize()
+    assert abs(float(f) - float(f_ref)) <= REL_TOL * abs(float(f_ref))
+    assert rel_err(g, g_ref) <= REL_TOL
