@@ -44,6 +44,27 @@ constexpr int kT1Rows = 32, kT2Rows = 48;
 constexpr int kT1Floats = kT1Rows * kN, kT2Floats = kT2Rows * kN;
 constexpr int kImgAllFloats = kImgFloats + 2 * (kT1Floats + kT2Floats);  // + T1h | T1l | T2h | T2l
 constexpr int kImgAllBytes = kImgAllFloats * 4;  // 97280
+// Per-net geometry of the FORWARD kernel's A operand and weight image.  LSTM-20x2 with <= 3 features (identity,
+// LogAndSign): the constants above.  RNNProp (fc(2->20)+ELU, DM/networks.py:180-183,219): the feature chunk widens to
+// 24 columns [u(20) | 1 | 0 0 0], the row becomes [chunk | h1 | h2] = 64 columns; layer 1 contracts columns [0,48)
+// (the h2 units 0..3 at 44..47 meet zero weight rows) and layer 2 columns [16,64) (u16..19 meet zero rows, the
+// constant 1 at column 20 carries b2) -- both K = 48, the same trick the BPTT kernel uses for its Z2.
+template <class C>
+struct Geo {
+  static constexpr bool FC = C::FC;
+  static constexpr int XC = FC ? 24 : kXC;
+  static constexpr int ColH1 = XC, ColH2 = XC + kH;
+  static constexpr int ACols = FC ? 64 : kACols;
+  static constexpr int K1 = FC ? 48 : kK1;
+  static constexpr int K2 = 48;
+  static constexpr int A2Off = FC ? 16 : 0;          // first A column of the layer-2 contraction
+  static constexpr int TileCols = kN + 2 * ACols;    // D | A_hi | A_lo
+  static constexpr int B1Floats = K1 * kN, B2Floats = K2 * kN;
+  static constexpr int ImgFloats = 2 * (B1Floats + B2Floats);
+  static constexpr int ImgBytes = ImgFloats * 4;
+  static_assert(kTiles * TileCols <= kTmemCols, "TMEM budget");
+  static_assert(!FC || C::F == 20, "fc preprocessing: dim 20");
+};
 constexpr uint32_t kSBO = 128;               // bytes between 8-row (N) core-matrix groups
 constexpr uint32_t kLBO = (kN / 8) * 128;    // bytes between 16-byte K chunks
 
@@ -280,19 +301,21 @@ __device__ __forceinline__ int timg_index(int nrows, int nprime, int kprime) {
   return ((kprime >> 2) * (nrows / 8) + (nprime >> 3)) * 32 + (nprime & 7) * 4 + (kprime & 3);
 }
 
-// value of the extended weight matrix of layer `l2` at (input row k = A column index, interleaved gate column n)
+// value of the extended weight matrix of layer `l2` at (row k of that layer's contraction range, interleaved gate
+// column n); A column = k (layer 1) or Geo::A2Off + k (layer 2)
 template <class C>
 __device__ __forceinline__ float ext_weight(const float* __restrict__ theta, bool l2, int k, int n) {
+  using G = Geo<C>;
   const int u = n >> 2, g = n & 3;
   const int col = g * kH + u;  // reference gate-column order i|j|f|o blocks (snt.LSTM split)
+  const int ac = l2 ? G::A2Off + k : k;
+  if (ac == C::F) return theta[(l2 ? C::O_B2 : C::O_B1) + col];
   if (!l2) {
-    if (k < C::F) return theta[C::O_W1 + k * C::G1 + col];
-    if (k == C::F) return theta[C::O_B1 + col];
-    if (k >= kColH1 && k < kColH1 + kH) return theta[C::O_W1 + (C::F + k - kColH1) * C::G1 + col];
+    if (ac < C::F) return theta[C::O_W1 + ac * C::G1 + col];
+    if (ac >= G::ColH1 && ac < G::ColH1 + kH) return theta[C::O_W1 + (C::F + ac - G::ColH1) * C::G1 + col];
     return 0.f;
   }
-  if (k == C::F) return theta[C::O_B2 + col];
-  if (k >= kColH1 && k < kColH1 + 2 * kH) return theta[C::O_W2 + (k - kColH1) * C::G2 + col];
+  if (ac >= G::ColH1 && ac < G::ColH1 + 2 * kH) return theta[C::O_W2 + (ac - G::ColH1) * C::G2 + col];
   return 0.f;
 }
 
@@ -320,40 +343,61 @@ __device__ __forceinline__ float ext_weight_bwd(const float* __restrict__ theta,
 constexpr float kLog2e = 1.4426950408889634f;
 template <class C>
 __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __restrict__ img, int with_transposed) {
-  static_assert(C::H1 == kH && C::H2 == kH && C::F <= 3 && !C::FC, "tc engine: LSTM-20x2, F <= 3");
-  float* b1h = img;
-  float* b1l = img + kB1Floats;
-  float* b2h = img + 2 * kB1Floats;
-  float* b2l = img + 2 * kB1Floats + kB2Floats;
-  float* t1h = img + kImgFloats;
-  float* t1l = t1h + kT1Floats;
-  float* t2h = t1l + kT1Floats;
-  float* t2l = t2h + kT2Floats;
-  const int nfwd = (kK1 + kK2) * kN;
-  const int ntr = with_transposed ? (kT1Rows + kT2Rows) * kN : 0;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nfwd + ntr; e += gridDim.x * blockDim.x) {
-    float hi, lo;
-    if (e < nfwd) {
-      const bool l2 = e >= kK1 * kN;
-      const int ee = l2 ? e - kK1 * kN : e;
+  static_assert(C::H1 == kH && C::H2 == kH && (C::F <= 3 || C::FC), "tc engine: LSTM-20x2, F <= 3 or fc(20)");
+  using G = Geo<C>;
+  if (!with_transposed) {   // forward image: B1h | B1l | B2h | B2l in the net's own geometry
+    float* b1h = img;
+    float* b1l = img + G::B1Floats;
+    float* b2h = img + 2 * G::B1Floats;
+    float* b2l = img + 2 * G::B1Floats + G::B2Floats;
+    const int nfwd = (G::K1 + G::K2) * kN;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nfwd; e += gridDim.x * blockDim.x) {
+      const bool l2 = e >= G::K1 * kN;
+      const int ee = l2 ? e - G::K1 * kN : e;
       const int k = ee / kN, n = ee % kN;
-      const float w = with_transposed ? ext_weight_bwd<C>(theta, l2, k, n) : ext_weight<C>(theta, l2, k, n);
-      hi = to_tf32(w);
-      lo = w - hi;
+      const float w = ext_weight<C>(theta, l2, k, n);
+      const float hi = to_tf32(w);
       const int idx = img_index(k, n);
       (l2 ? b2h : b1h)[idx] = hi;
-      (l2 ? b2l : b1l)[idx] = to_tf32(lo);
-    } else {
-      const int e2 = e - nfwd;
-      const bool l2 = e2 >= kT1Rows * kN;
-      const int ee = l2 ? e2 - kT1Rows * kN : e2;
-      const int k = ee / kN, n = ee % kN;  // k = input row (n'), n = gate (k')
-      const float w = (k < (l2 ? kK2 : kK1)) ? ext_weight_bwd<C>(theta, l2, k, n) : 0.f;
-      hi = to_tf32(w);
-      lo = w - hi;
-      const int idx = timg_index(l2 ? kT2Rows : kT1Rows, k, n);
-      (l2 ? t2h : t1h)[idx] = hi;
-      (l2 ? t2l : t1l)[idx] = to_tf32(lo);
+      (l2 ? b2l : b1l)[idx] = to_tf32(w - hi);
+    }
+    return;
+  }
+  if constexpr (!C::FC) {   // BPTT image (B1' | B2' in the BPTT operand order, then T1 | T2)
+    float* b1h = img;
+    float* b1l = img + kB1Floats;
+    float* b2h = img + 2 * kB1Floats;
+    float* b2l = img + 2 * kB1Floats + kB2Floats;
+    float* t1h = img + kImgFloats;
+    float* t1l = t1h + kT1Floats;
+    float* t2h = t1l + kT1Floats;
+    float* t2l = t2h + kT2Floats;
+    const int nfwd = (kK1 + kK2) * kN;
+    const int ntr = (kT1Rows + kT2Rows) * kN;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nfwd + ntr; e += gridDim.x * blockDim.x) {
+      float hi, lo;
+      if (e < nfwd) {
+        const bool l2 = e >= kK1 * kN;
+        const int ee = l2 ? e - kK1 * kN : e;
+        const int k = ee / kN, n = ee % kN;
+        const float w = ext_weight_bwd<C>(theta, l2, k, n);
+        hi = to_tf32(w);
+        lo = w - hi;
+        const int idx = img_index(k, n);
+        (l2 ? b2h : b1h)[idx] = hi;
+        (l2 ? b2l : b1l)[idx] = to_tf32(lo);
+      } else {
+        const int e2 = e - nfwd;
+        const bool l2 = e2 >= kT1Rows * kN;
+        const int ee = l2 ? e2 - kT1Rows * kN : e2;
+        const int k = ee / kN, n = ee % kN;  // k = input row (n'), n = gate (k')
+        const float w = (k < (l2 ? kK2 : kK1)) ? ext_weight_bwd<C>(theta, l2, k, n) : 0.f;
+        hi = to_tf32(w);
+        lo = w - hi;
+        const int idx = timg_index(l2 ? kT2Rows : kT1Rows, k, n);
+        (l2 ? t2h : t1h)[idx] = hi;
+        (l2 ? t2l : t1l)[idx] = to_tf32(lo);
+      }
     }
   }
 }
@@ -407,9 +451,19 @@ __device__ __forceinline__ void lstm_unit_fwd(const float* z, float& c, float& h
   lstm_point_fwd(z[0], z[1], z[2], z[3], c, h);
 }
 
+// internal (non-ABI) extras of a launch: RNNProp's bias-correction exponent p = float(step0 + t) may come from a
+// DEVICE scalar (l2o_step_args::step_ptr, CUDA-graph friendly) or a fixed float (l2o_step_args::p)
+struct FwdExtra {
+  const int32_t* step_ptr;   // non-NULL: step0 = *step_ptr + t_offset
+  int32_t t_offset;
+  float p_fixed;             // used when > 0 and step_ptr == NULL (single step)
+};
+
+template <class C>
 struct Smem {
-  float img[kImgFloats];          // must stay first (16B-aligned TMA destination, descriptor base)
+  float img[Geo<C>::ImgFloats];   // must stay first (16B-aligned TMA destination, descriptor base)
   float wo[kH + 4];               // linear/w, linear/b
+  float win[64];                  // fc nets: input_projection/w [2][20] then /b [20]
   float ypart[kTiles][2][128];    // output-layer partial sums exchanged inside a thread pair
   uint64_t wbar;
   uint64_t a_ready[kTiles];
@@ -424,15 +478,23 @@ struct Smem {
 // it.  Two buffers x kTiles tiles x 4 arrays (h1, c1, h2, c2) x [128][kH] floats = 160 KB after the fx tail.
 constexpr int kStageArr = 128 * kH;                       // floats per (tile, array)
 constexpr int kStageFloats = 2 * kTiles * 4 * kStageArr;  // 40960 floats
+// dynamic tail after Smem<C>: fx [T+1] doubles | (fc nets) Adam bias corrections [T][2] floats | staging buffers
+template <class C>
+__host__ __device__ constexpr size_t adamc_offset(int T) {
+  return (sizeof(Smem<C>) + (size_t)(T + 1) * sizeof(double) + 15) & ~(size_t)15;
+}
+template <class C>
 __host__ __device__ constexpr size_t stage_offset(int T) {
-  return (sizeof(Smem) + (size_t)(T + 1) * sizeof(double) + 127) & ~(size_t)127;
+  return (adamc_offset<C>(T) + (C::FC ? (size_t)T * 2 * sizeof(float) : 0) + 127) & ~(size_t)127;
 }
 
 // Epilogue of one thread: coordinate `row` of tile `tile`, hidden units [U0, U0+NU) of both layers.
 template <class C, int HALF, bool STAGE>
-__device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const NetRt& rt, Smem& S, uint32_t tmem_base,
+__device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const NetRt& rt, Smem<C>& S, uint32_t tmem_base,
                                              float* __restrict__ state_out, int warp, int lane,
-                                             const float* __restrict__ stage) {
+                                             const float* __restrict__ stage, const float* __restrict__ adamc) {
+  using G = Geo<C>;
+  constexpr int kTileCols = G::TileCols, kACols = G::ACols, kColH1 = G::ColH1, kColH2 = G::ColH2;  // shadow the defaults
   constexpr int U0 = HalfUnits<HALF>::U0;
   constexpr int NU = HalfUnits<HALF>::NU;
   const int tile = warp >> 3;          // warps 0-7: tile 0, 8-15: tile 1
@@ -450,10 +512,11 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
   uint32_t pd = 0;  // d_ready parity
   const int64_t slot = n * C::SF;
   double imit = 0.0;
-  if (HALF == 1) {  // zero the 4 pad columns of A once (they meet zero weight rows, but must be finite)
+  if (HALF == 1 && kColH2 + kH < kACols) {  // zero the pad columns of A once (zero weight rows, but must be finite)
     tmem_st4(t_ah + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
     tmem_st4(t_al + kColH2 + kH, 0.f, 0.f, 0.f, 0.f);
   }
+  const bool adam_mode = C::NIN == 2 && a.m != nullptr;   // fused RNNProp features (DM/meta_rnnprop_train.py:383-388)
   uint32_t pfull[2] = {0, 0};
   int kpair = 0;
   for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++kpair) {
@@ -474,6 +537,8 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
     }
     float c1[NU], c2[NU];
     float x = 0.f, oa = 0.f, ob = 0.f;
+    float am = 0.f, av = 0.f;   // RNNProp Adam moments of this coordinate (half 1)
+    if (HALF == 1 && adam_mode && act) { am = a.m[i]; av = a.v[i]; }
     {
       float h1[NU], h2[NU];
 #pragma unroll
@@ -514,22 +579,58 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       // ---- gradient + preprocessing -> feature chunk of A (half 1 owns the per-coordinate scalars) ----------
       float fval = 0.f;
       if (HALF == 1) {
-        float raw0 = 0.f;
+        float raw0 = 0.f, raw1 = 0.f;
         if (act) {
           if (in_kernel_opt) {
             optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, raw0);
             if (a.g_rec) a.g_rec[(int64_t)t * n + i] = raw0;
+          } else if (C::NIN == 2 && !adam_mode) {   // operator surface: (m~, g~) given
+            raw0 = a.in_seq[((int64_t)t * 2) * n + i];
+            raw1 = a.in_seq[((int64_t)t * 2 + 1) * n + i];
           } else {
             raw0 = a.in_seq[(int64_t)t * n + i];
           }
         }
-        float u[4] = {0.f, 0.f, 0.f, 0.f};
-        float dummy[C::F];
-        preprocess<C>(nullptr, rt, raw0, 0.f, dummy);
+        if constexpr (C::FC) {
+          if (adam_mode) {   // m' = b1 m + (1-b1) g ; v' = b2 v + (1-b2) g^2 ; m~ = m^/(sqrt(v^)+1e-8) ; g~ = g/(sqrt(v^)+1e-8)
+            const float g = raw0;
+            am = a.beta1 * am + (1.0f - a.beta1) * g;
+            av = a.beta2 * av + (1.0f - a.beta2) * g * g;
+            const float mh = am / adamc[2 * t], vh = av / adamc[2 * t + 1];   // 1 - beta^p, tabulated per step
+            const float den = sqrtf(vh) + 1e-8f;
+            raw0 = mh / den;
+            raw1 = g / den;
+          }
+          if (act && a.feat_rec) {
+            a.feat_rec[((int64_t)t * 2) * n + i] = raw0;
+            a.feat_rec[((int64_t)t * 2 + 1) * n + i] = raw1;
+          }
+          // u = elu([m~, g~] Win + bin) (DM/networks.py:219), then the constant 1 and three zero columns
 #pragma unroll
-        for (int k = 0; k < C::F; ++k) u[k] = dummy[k];
-        u[C::F] = 1.0f;  // bias column
-        st_split4(t_ah, t_al, 0, u);
+          for (int k4 = 0; k4 < 5; ++k4) {
+            float u[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * k4 + e;
+              const float av_ = fmaf(raw1, S.win[20 + j], fmaf(raw0, S.win[j], S.win[40 + j]));
+              // elu: a (a > 0) | expm1(a); near zero the 2^x - 1 form cancels, so a short Taylor sum takes over
+              const float em = ex2_approx(kLog2e * av_) - 1.0f;
+              const float ep = av_ * fmaf(av_, fmaf(av_, fmaf(av_, 1.0f / 24.0f, 1.0f / 6.0f), 0.5f), 1.0f);
+              u[e] = av_ > 0.f ? av_ : (av_ > -0.0625f ? ep : em);
+            }
+            st_split4(t_ah, t_al, 4 * k4, u);
+          }
+          tmem_st4(t_ah + 20, 1.0f, 0.f, 0.f, 0.f);
+          tmem_st4(t_al + 20, 0.f, 0.f, 0.f, 0.f);
+        } else {
+          float u[4] = {0.f, 0.f, 0.f, 0.f};
+          float dummy[C::F];
+          preprocess<C>(nullptr, rt, raw0, 0.f, dummy);
+#pragma unroll
+          for (int k = 0; k < C::F; ++k) u[k] = dummy[k];
+          u[C::F] = 1.0f;  // bias column
+          st_split4(t_ah, t_al, 0, u);
+        }
       }
       tc_wait_st();
       tc_fence_before();
@@ -620,6 +721,7 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
           store_units<HALF>(state_out + 2 * n * kH + (n + i) * kH + U0, c2);
         }
         if (HALF == 1 && a.x) a.x[i] = x;
+        if (HALF == 1 && adam_mode) { a.m[i] = am; a.v[i] = av; }
       }
       if (HALF == 1 && want_fx) {
         const double ws = warp_sum_d((double)fval);
@@ -635,9 +737,10 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
 
 template <class C, bool STAGE>
 __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args a, NetRt rt, const float* __restrict__ img,
-                                                                  float* __restrict__ state_out) {
+                                                                  float* __restrict__ state_out, FwdExtra ex) {
+  using G = Geo<C>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  Smem<C>& S = *reinterpret_cast<Smem<C>*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = a.T;
   const int64_t n = a.n;
@@ -649,6 +752,19 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
     for (int t = threadIdx.x; t <= T; t += blockDim.x) S.fx[t] = 0.0;
   if (threadIdx.x < kH) S.wo[threadIdx.x] = a.theta[C::O_WO + threadIdx.x];
   if (threadIdx.x == kH) S.wo[kH] = a.theta[C::O_BO];
+  float* adamc = reinterpret_cast<float*>(smem_raw + adamc_offset<C>(T));
+  if constexpr (C::FC) {
+    static_assert(!C::FC || C::NIN == 2, "fc nets here are RNNprop nets (two inputs)");
+    if (threadIdx.x < 60) S.win[threadIdx.x] = a.theta[C::O_WIN + threadIdx.x];   // w [2][20] then b [20] (contiguous)
+    if (a.m != nullptr) {   // 1 - beta^p per step, p = float(step + t) (DM/meta_rnnprop_train.py:384,386)
+      const int step0 = ex.step_ptr ? *ex.step_ptr + ex.t_offset : a.step0;
+      for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const float p = (ex.step_ptr == nullptr && ex.p_fixed > 0.f) ? ex.p_fixed : (float)(step0 + t);
+        adamc[2 * t] = 1.0f - powf(a.beta1, p);
+        adamc[2 * t + 1] = 1.0f - powf(a.beta2, p);
+      }
+    }
+  }
   if (warp == kIssuerWarp) {
     if (lane == 0) {
       mbar_init(&S.wbar, 1);
@@ -667,8 +783,8 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
     tmem_alloc(&S.tmem_slot, kTmemCols);
     tmem_relinquish();
     if (lane == 0) {
-      mbar_expect_tx(&S.wbar, kImgBytes);
-      tma_bulk_g2s(S.img, img, kImgBytes, &S.wbar);
+      mbar_expect_tx(&S.wbar, G::ImgBytes);
+      tma_bulk_g2s(S.img, img, G::ImgBytes, &S.wbar);
     }
   }
   tc_fence_before();
@@ -679,15 +795,15 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
   if (warp < kIssuerWarp) {
     // =============================== epilogue warps: a thread pair per coordinate ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFwdEpiRegs));
-    const float* stage = reinterpret_cast<const float*>(smem_raw + stage_offset(T));
-    if (((warp >> 2) & 1) == 0) fwd_epilogue<C, 0, STAGE>(a, rt, S, tmem_base, state_out, warp, lane, stage);
-    else fwd_epilogue<C, 1, STAGE>(a, rt, S, tmem_base, state_out, warp, lane, stage);
+    const float* stage = reinterpret_cast<const float*>(smem_raw + stage_offset<C>(T));
+    if (((warp >> 2) & 1) == 0) fwd_epilogue<C, 0, STAGE>(a, rt, S, tmem_base, state_out, warp, lane, stage, adamc);
+    else fwd_epilogue<C, 1, STAGE>(a, rt, S, tmem_base, state_out, warp, lane, stage, adamc);
   } else if (warp > kIssuerWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFwdIssuerRegs));  // idle warps of the issuer warpgroup
     if constexpr (STAGE) {
       if (warp == kIssuerWarp + 1) {
         // ---- state-row producer: TMA bulk copies of pair k+0, k+1 ... into the two staging buffers -------------------
-        float* stage = reinterpret_cast<float*>(smem_raw + stage_offset(T));
+        float* stage = reinterpret_cast<float*>(smem_raw + stage_offset<C>(T));
         uint32_t pempty[2] = {0, 0};
         int k = 0;
         for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++k) {
@@ -730,9 +846,9 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
     const uint32_t idesc = make_idesc(kN);
     const uint32_t img_s = smem_u32(S.img);
     const uint64_t b1h = make_bdesc(img_s);
-    const uint64_t b1l = make_bdesc(img_s + kB1Floats * 4);
-    const uint64_t b2h = make_bdesc(img_s + 2 * kB1Floats * 4);
-    const uint64_t b2l = make_bdesc(img_s + (2 * kB1Floats + kB2Floats) * 4);
+    const uint64_t b1l = make_bdesc(img_s + G::B1Floats * 4);
+    const uint64_t b2h = make_bdesc(img_s + 2 * G::B1Floats * 4);
+    const uint64_t b2l = make_bdesc(img_s + (2 * G::B1Floats + G::B2Floats) * 4);
     constexpr uint64_t kStep = (2 * kLBO) >> 4;  // descriptor start-address increment per K=8 chunk
     uint32_t pa[kTiles] = {0, 0};
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
@@ -741,26 +857,26 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
         for (int layer = 0; layer < 2; ++layer) {
 #pragma unroll
           for (int tile = 0; tile < kTiles; ++tile) {
-            const uint32_t t_d = tmem_base + tile * kTileCols;
+            const uint32_t t_d = tmem_base + tile * G::TileCols;
             const uint32_t t_ah = t_d + kN;
-            const uint32_t t_al = t_ah + kACols;
+            const uint32_t t_al = t_ah + G::ACols;
             mbar_wait(&S.a_ready[tile], pa[tile]);
             pa[tile] ^= 1;
             tc_fence_after();
             if (elect_one()) {
               if (layer == 0) {
 #pragma unroll
-                for (int kc = 0; kc < kK1 / 8; ++kc) {
+                for (int kc = 0; kc < G::K1 / 8; ++kc) {
                   mma_tf32_ts(t_d, t_al + 8 * kc, b1h + kc * kStep, idesc, kc > 0 ? 1u : 0u);
                   mma_tf32_ts(t_d, t_ah + 8 * kc, b1l + kc * kStep, idesc, 1u);
                   mma_tf32_ts(t_d, t_ah + 8 * kc, b1h + kc * kStep, idesc, 1u);
                 }
               } else {
 #pragma unroll
-                for (int kc = 0; kc < kK2 / 8; ++kc) {
-                  mma_tf32_ts(t_d, t_al + 8 * kc, b2h + kc * kStep, idesc, kc > 0 ? 1u : 0u);
-                  mma_tf32_ts(t_d, t_ah + 8 * kc, b2l + kc * kStep, idesc, 1u);
-                  mma_tf32_ts(t_d, t_ah + 8 * kc, b2h + kc * kStep, idesc, 1u);
+                for (int kc = 0; kc < G::K2 / 8; ++kc) {
+                  mma_tf32_ts(t_d, t_al + G::A2Off + 8 * kc, b2h + kc * kStep, idesc, kc > 0 ? 1u : 0u);
+                  mma_tf32_ts(t_d, t_ah + G::A2Off + 8 * kc, b2l + kc * kStep, idesc, 1u);
+                  mma_tf32_ts(t_d, t_ah + G::A2Off + 8 * kc, b2h + kc * kStep, idesc, 1u);
                 }
               }
               tc_commit(&S.d_ready[tile]);
@@ -785,17 +901,17 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
 // ------------------------------------------------------------------ host side (called from l2o_capi.cu)
 template <class C>
 int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms, float* state_out = nullptr,
-                  bool stage = false) {
+                  bool stage = false, tc::FwdExtra ex = tc::FwdExtra{nullptr, 0, 0.f}) {
   tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 0);
   // stage: TMA-prefetched state rows (the l2o_step path, T = 1); needs 16-byte aligned arrays (n * 80 B always is)
   stage = stage && (reinterpret_cast<uintptr_t>(a.state) % 16 == 0);
   auto k = stage ? tc::unroll_fwd_kernel<C, true> : tc::unroll_fwd_kernel<C, false>;
-  const size_t smem = tc::stage_offset(a.T) + (stage ? (size_t)tc::kStageFloats * sizeof(float) : 0) + 128;
+  const size_t smem = tc::stage_offset<C>(a.T) + (stage ? (size_t)tc::kStageFloats * sizeof(float) : 0) + 128;
   if (smem > 227 * 1024) return L2O_E_INVALID;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
   const int64_t npairs = (a.n + tc::kTileCoords - 1) / tc::kTileCoords;
   const int grid = (int)(npairs < sms ? npairs : sms);
-  k<<<grid, tc::kThreads, smem, st>>>(a, rt, img, state_out ? state_out : a.state);
+  k<<<grid, tc::kThreads, smem, st>>>(a, rt, img, state_out ? state_out : a.state, ex);
   return cudaGetLastError() == cudaSuccess ? L2O_OK : L2O_E_CUDA;
 }
 

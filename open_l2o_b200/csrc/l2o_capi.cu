@@ -150,7 +150,7 @@ int l2o_unroll_fwd(l2o_handle h, const l2o_unroll_args* a, void* stream) {
   if (a->labels && (!a->imit_loss || a->n_total <= 0)) return L2O_E_INVALID;
   if (a->n == 0) return L2O_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc_can = l2o::tc_supported(h->cfg) && l2o::tc_fwd_ok(*a);
+  const bool tc_can = l2o::tc_supported(h->cfg) && l2o::tc_fwd_ok(h, *a);
   if (h->engine == L2O_ENGINE_TC) return tc_can ? l2o::tc_unroll_fwd(h, *a, st) : L2O_E_UNSUPPORTED;
   if (h->engine == L2O_ENGINE_AUTO && tc_can && l2o::tc_auto_default()) return l2o::tc_unroll_fwd(h, *a, st);
   return l2o::ffma_unroll_fwd(h, *a, st);

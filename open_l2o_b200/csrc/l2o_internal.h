@@ -36,7 +36,7 @@ int ffma_unroll_fwd(const l2o_net* h, const l2o_unroll_args& a, cudaStream_t st)
 int ffma_unroll_bwd(const l2o_net* h, const l2o_bwd_args& a, cudaStream_t st);
 
 bool tc_supported(int cfg);
-bool tc_fwd_ok(const l2o_unroll_args& a);
+bool tc_fwd_ok(const l2o_net* h, const l2o_unroll_args& a);
 int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st);
 bool tc_step_ok(const l2o_net* h, const l2o_step_args& a);
 int tc_step(l2o_net* h, const l2o_step_args& a, cudaStream_t st);

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("name", ["dm_identity", "dm_logsign"])
+@pytest.mark.parametrize("name", ["dm_identity", "dm_logsign", "rnnprop"])
 @pytest.mark.parametrize("n,T", [(777, 20), (256, 1), (5000, 3)])
 def test_tc_unroll_fwd_prerecorded(name, n, T):
     from open_l2o_b200.engine import ENGINE_TC
@@ -182,3 +182,73 @@ def test_tc_imitation_bptt(name):
     assert rel_err(dtheta, g64) <= slack, (rel_err(dtheta, g64), rel_err(g32, g64))
     with pytest.raises(Exception):   # imitation mode without the recorded deltas is not a tensor-core mode
         h.unroll_bwd(th, n, T, seq, ckpt, dtheta, labels=lab, n_total=n)
+
+
+def test_tc_rnnprop_step_fused_adam_features():
+    """RNNProp (DM/networks.py:279-300 + DM/meta_rnnprop_train.py:383-388) on the tcgen05 engine: l2o_step with the
+    fused Adam-feature mode (m, v in/out, p from a DEVICE scalar as the captured graphs use it), fc(2->20)+ELU in the
+    epilogue, tanh output; three chained steps against the oracle, incl. the recorded (m~, g~) rows."""
+    from open_l2o_b200.engine import ENGINE_TC
+    from tests.helpers import random_state, state_to_arena
+    spec = SPECS["rnnprop"]
+    n = 20000 + 37
+    gen = torch.Generator().manual_seed(41)
+    theta = _theta(spec)
+    st = random_state(spec, n, gen)
+    x_ref = torch.randn(n, generator=gen)
+    m_ref, v_ref = torch.zeros(n), torch.zeros(n)
+    h = make_handle(spec)
+    h.set_engine(ENGINE_TC)
+    th = theta.to(DEV)
+    a_in = state_to_arena(st, n).to(DEV)
+    x = x_ref.to(DEV).clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step_dev = torch.tensor([5], dtype=torch.int32, device=DEV)
+    for it in range(3):
+        g = torch.randn(n, generator=gen) * (10.0 ** float(torch.randint(-4, 1, (1,), generator=gen)))
+        g[::13] = 0.0
+        m_ref, v_ref, mt, gt = orc.adam_features(g, m_ref, v_ref, float(5 + it), 0.95, 0.95)
+        d_ref, st = orc.net_apply(spec, theta, torch.stack([mt, gt], -1), st)
+        x_ref = x_ref + d_ref
+        a_out = torch.zeros_like(a_in)
+        delta = torch.empty(n, device=DEV)
+        feat = torch.empty(2, n, device=DEV)
+        h.step(th, g.to(DEV), a_in, a_out, m=m, v=v, beta1=0.95, beta2=0.95, x=x, delta=delta, feat_out=feat,
+               step_ptr=step_dev, t_offset=it)
+        torch.cuda.synchronize()
+        assert rel_err(feat[0], mt) <= REL_TOL and rel_err(feat[1], gt) <= REL_TOL
+        assert rel_err(m, m_ref) <= REL_TOL and rel_err(v, v_ref) <= REL_TOL
+        assert rel_err(delta, d_ref) <= REL_TOL
+        assert rel_err(x, x_ref) <= REL_TOL
+        for (hg, cg), (hr, cr) in zip(arena_to_state(a_out.cpu(), spec.layers, n), st):
+            assert rel_err(hg, hr) <= REL_TOL and rel_err(cg, cr) <= REL_TOL
+        a_in = a_out
+
+
+def test_tc_rnnprop_fused_unroll_matches_ffma():
+    """RNNProp fused unroll (in-kernel separable optimizee, Adam moments carried in registers, checkpoints and
+    (m~, g~) rows recorded) on the tcgen05 engine vs the exact-fp32 engine, multi-tile with a ragged tail."""
+    from open_l2o_b200.engine import ENGINE_FFMA, ENGINE_TC, OPT_KINDS
+    spec = SPECS["rnnprop"]
+    n, T = 148 * 256 + 91, 6
+    gen = torch.Generator().manual_seed(9)
+    theta = _theta(spec).to(DEV)
+    a, b, x0 = (torch.randn(n, generator=gen).to(DEV) for _ in range(3))
+    outs = {}
+    for eng in (ENGINE_FFMA, ENGINE_TC):
+        h = make_handle(spec)
+        h.set_engine(eng)
+        arena = h.new_state(n, DEV)
+        x = x0.clone()
+        m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        fx = torch.zeros(T + 1, dtype=torch.float64, device=DEV)
+        g_rec = torch.empty(T + 1, n, device=DEV)
+        feat = torch.empty(T, 2, n, device=DEV)
+        ckpt = torch.zeros((T + 1) * h.state_floats * n, device=DEV)
+        h.unroll_fwd(theta, n, T, arena, opt_kind=OPT_KINDS["rastrigin_sep"], opt_a=a, opt_b=b, opt_alpha=10.0,
+                     opt_fscale=1.0 / n, x=x, ckpt=ckpt, m=m, v=v, beta1=0.95, beta2=0.95, step0=3, g_rec=g_rec,
+                     feat_rec=feat, fx=fx)
+        torch.cuda.synchronize()
+        outs[eng] = (x, arena, fx, g_rec, feat, m, v, ckpt)
+    for u, w in zip(outs[ENGINE_TC], outs[ENGINE_FFMA]):
+        assert rel_err(u, w) <= REL_TOL
