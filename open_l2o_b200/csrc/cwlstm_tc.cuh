@@ -251,6 +251,20 @@ __device__ __forceinline__ void load_units(const float* __restrict__ p, float* v
     }
   });
 }
+// the same from a shared-window address (explicit ld.shared: no generic-window check per access)
+template <int HALF>
+__device__ __forceinline__ void load_units_smem(uint32_t sa, float* v) {
+  for_chunks<HALF>([&](auto k0c, auto ncc) {
+    L2O_CHUNK(K0, NC, k0c, ncc);
+    if constexpr (NC == 4) {
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[K0]), "=f"(v[K0 + 1]), "=f"(v[K0 + 2]), "=f"(v[K0 + 3])
+                   : "r"(sa + 4u * K0));
+    } else {
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[K0]), "=f"(v[K0 + 1]) : "r"(sa + 4u * K0));
+    }
+  });
+}
 template <int HALF>
 __device__ __forceinline__ void store_units(float* __restrict__ p, const float* v) {
   for_chunks<HALF>([&](auto k0c, auto ncc) {
@@ -548,11 +562,11 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
         mbar_wait(&S.full[buf], pfull[buf]);
         pfull[buf] ^= 1;
         if (act) {
-          const float* sb = stage + (size_t)((buf * kTiles + tile) * 4) * kStageArr + row * kH + U0;
-          load_units<HALF>(sb, h1);
-          load_units<HALF>(sb + kStageArr, c1);
-          load_units<HALF>(sb + 2 * kStageArr, h2);
-          load_units<HALF>(sb + 3 * kStageArr, c2);
+          const uint32_t sb = smem_u32(stage) + 4u * (uint32_t)(((buf * kTiles + tile) * 4) * kStageArr + row * kH + U0);
+          load_units_smem<HALF>(sb, h1);
+          load_units_smem<HALF>(sb + 4u * kStageArr, c1);
+          load_units_smem<HALF>(sb + 8u * kStageArr, h2);
+          load_units_smem<HALF>(sb + 12u * kStageArr, c2);
         }
         mbar_arrive(&S.empty[buf]);   // release: the producer may refill this buffer (two pairs ahead)
       }

@@ -156,27 +156,37 @@ __device__ __forceinline__ uint32_t y16_off(int c, int s) {
   return (uint32_t)((s >> 6) * (int)kLBO16 + (c >> 3) * (int)kSBO16 + (c & 7) * 128 + ((((s & 63) >> 3) ^ (c & 7)) << 4) +
                     (s & 7) * 2);
 }
-// NV values (2, 4 or 8) -> slots [s, s+NV) of coordinate c in the hi / lo buffers
+// explicit shared-window stores (a generic store to a shared address pays the window check on every access)
+__device__ __forceinline__ void sts128(uint32_t sa, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t sa, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t sa, uint32_t a) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa), "r"(a) : "memory");
+}
+// NV values (2, 4 or 8) -> slots [s, s+NV) of coordinate c in the hi / lo buffers (yh, yl: shared-window addresses)
 template <int NV>
-__device__ __forceinline__ void stage16(unsigned char* yh, unsigned char* yl, int c, int s, const float* v) {
+__device__ __forceinline__ void stage16(uint32_t yh, uint32_t yl, int c, int s, const float* v) {
   const uint32_t off = y16_off(c, s);
   uint32_t h[NV / 2], l[NV / 2];
 #pragma unroll
   for (int k = 0; k < NV / 2; ++k) split_bf16x2(v[2 * k], v[2 * k + 1], h[k], l[k]);
   if constexpr (NV == 8) {
-    *reinterpret_cast<uint4*>(yh + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(yl + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    sts128(yh + off, h[0], h[1], h[2], h[3]);
+    sts128(yl + off, l[0], l[1], l[2], l[3]);
   } else if constexpr (NV == 4) {
-    *reinterpret_cast<uint2*>(yh + off) = make_uint2(h[0], h[1]);
-    *reinterpret_cast<uint2*>(yl + off) = make_uint2(l[0], l[1]);
+    sts64(yh + off, h[0], h[1]);
+    sts64(yl + off, l[0], l[1]);
   } else {
-    *reinterpret_cast<uint32_t*>(yh + off) = h[0];
-    *reinterpret_cast<uint32_t*>(yl + off) = l[0];
+    sts32(yh + off, h[0]);
+    sts32(yl + off, l[0]);
   }
 }
 // the thread's 10 per-unit values -> slots [s0 + U0, s0 + U0 + 10)
 template <int HALF>
-__device__ __forceinline__ void stage_units10(unsigned char* yh, unsigned char* yl, int c, int s0, const float* v) {
+__device__ __forceinline__ void stage_units10(uint32_t yh, uint32_t yl, int c, int s0, const float* v) {
   constexpr int U0 = HALF * kNU;
   chunks10<HALF>([&](auto k0c, auto ncc) {
     L2O_CHUNK(K0, NC, k0c, ncc);
@@ -185,7 +195,7 @@ __device__ __forceinline__ void stage_units10(unsigned char* yh, unsigned char* 
 }
 // re-read this thread's dZ columns (hi part == the exact fp32 value, see split_tf32) and stage them as bf16 hi/lo
 template <int HALF>
-__device__ __forceinline__ void stage_dz(uint32_t t_z, unsigned char* yh, unsigned char* yl, int c) {
+__device__ __forceinline__ void stage_dz(uint32_t t_z, uint32_t yh, uint32_t yl, int c) {
   constexpr int U0 = HALF * kNU;
   chunks10<HALF>([&](auto k0c, auto ncc) {
     L2O_CHUNK(K0, NC, k0c, ncc);
@@ -233,8 +243,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
   const int c = q * 32 + lane;
   const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t tZ = tl + cZ2, tRh = tl + cR2, tRl = tl + cR2 + kA2Cols, tDl = tl + cR2, tX = tl + cX2;
-  unsigned char* yh = reinterpret_cast<unsigned char*>(S.y2h);
-  unsigned char* yl = reinterpret_cast<unsigned char*>(S.y2l);
+  const uint32_t yh = smem_u32(S.y2h), yl = smem_u32(S.y2l);
   const int T = a.T;
   const int64_t n = a.n, slot = n * C::SF, ntiles = (n + 127) / 128;
   const bool imit = a.labels != nullptr;
@@ -396,8 +405,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
   const int c = q * 32 + lane;
   const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
   const uint32_t tZ = tl + cZ1, tRh = tl + cR1, tRl = tl + cR1 + kA1Cols, tDl = tl + cR1, tX = tl + cX1, tX2 = tl + cX2;
-  unsigned char* yh = reinterpret_cast<unsigned char*>(S.y1h);
-  unsigned char* yl = reinterpret_cast<unsigned char*>(S.y1l);
+  const uint32_t yh = smem_u32(S.y1h), yl = smem_u32(S.y1l);
   const int T = a.T;
   const int64_t n = a.n, slot = n * C::SF, ntiles = (n + 127) / 128;
   uint32_t pz = 0, px = 0, pw = 0, px2 = 0;
