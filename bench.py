@@ -162,7 +162,7 @@ def external_roofline(prog, netkind, T, t_unroll):
     r = prog.runs[0]
     h = r.net.handle
     n = r.n
-    slot = max(h.state_floats * n, 1)
+    slot = max(h.state_size(n), 1)
     xw = prog.X.clone()
     kw = {}
     if h.n_in == 2:

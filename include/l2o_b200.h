@@ -159,6 +159,54 @@ int l2o_adam_step(float* theta, const double* dtheta, float* m, float* v, int64_
 int l2o_log_and_sign(const float* g, float* out, int64_t n, float k, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Row-wise dense LSTM net with run-time shapes: StandardDeepLSTM with output_size > 1 = the reference's KernelDeepLSTM
+ * (DM/networks.py:154-236,303-351).  A convolution kernel [kw,kh,cin,cout] is R = cin*cout rows of K = kw*kh inputs;
+ * with the variable flat in its own order, element (k, r) sits at k*R + r.  theta: lstm_1/w_gates [F+H1,4H1], b_gates,
+ * lstm_2/..., linear/w [top, n_out], linear/b [n_out] (F = n_in, or 2*n_in interleaved (log, sign) with LogAndSign);
+ * state arena per layer: h [R][H] then c [R][H]; sequences [T][n_in][R]; g_rec [T+1][n_out][R].
+ *
+ *   l2o_dense_create / destroy / theta_count / state_floats   KernelDeepLSTM.__init__            DM/networks.py:311-323
+ *   l2o_dense_step        update, state' = net(kernel_gradient, state)  (+ x += update)          DM/networks.py:329-346
+ *   l2o_dense_unroll_bwd  tf.gradients through the unroll for this net         DM/meta.py:412 */
+typedef struct l2o_dense* l2o_dense_handle;
+typedef struct {
+  int32_t n_layers;    /* 0, 1 or 2 */
+  int32_t hidden[2];   /* <= 32 */
+  int32_t n_in;        /* K raw inputs per row (<= 64 with LogAndSign, <= 128 without) */
+  int32_t preprocess;  /* L2O_PRE_IDENTITY | L2O_PRE_LOGSIGN */
+  float logsign_k;
+  int32_t n_out;       /* outputs per row (<= 64) */
+  float scale;
+  int32_t tanh_output;
+} l2o_dense_desc;
+typedef struct {
+  int64_t rows;
+  const float* theta;
+  const float* in;       /* [n_in][rows] */
+  const float* state_in;
+  float* state_out;      /* may alias state_in */
+  float* x;              /* optional [n_out][rows]: x += update */
+  float* delta;          /* optional [n_out][rows] */
+} l2o_dense_step_args;
+typedef struct {
+  int64_t rows;
+  int32_t T;
+  const float* theta;
+  const float* in_seq;   /* [T][n_in][rows] */
+  const float* ckpt;     /* [T+1] state arenas, slot t = state BEFORE step t */
+  const float* g_rec;    /* [T+1][n_out][rows]: dUpdate_t = sum_{tau>t} g_tau ; NULL in imitation mode */
+  const float* labels;   /* imitation mode [T][n_out][rows] */
+  int64_t n_total;
+  double* dtheta;        /* [P] += */
+} l2o_dense_bwd_args;
+int l2o_dense_create(l2o_dense_handle* out, const l2o_dense_desc* desc);
+void l2o_dense_destroy(l2o_dense_handle h);
+int64_t l2o_dense_theta_count(l2o_dense_handle h);
+int64_t l2o_dense_state_floats(l2o_dense_handle h);   /* per ROW: 2*sum(H_l) */
+int l2o_dense_step(l2o_dense_handle h, const l2o_dense_step_args* a, void* stream);
+int l2o_dense_unroll_bwd(l2o_dense_handle h, const l2o_dense_bwd_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Fused gradient producers: f and df/dx of a synthetic optimizee family in ONE launch, replacing
  * the ~15 TF ops + tf.gradients of the reference's graph (DM/problems.py:103-175, DM/meta.py:322-329).
  *

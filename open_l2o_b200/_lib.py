@@ -25,6 +25,8 @@ ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
 EXPORTS = [
     "l2o_net_create", "l2o_net_destroy", "l2o_net_set_engine", "l2o_theta_count", "l2o_state_floats", "l2o_workspace_bytes",
     "l2o_step", "l2o_unroll_fwd", "l2o_unroll_bwd", "l2o_adam_step", "l2o_log_and_sign", "l2o_lasso_grad",
+    "l2o_dense_create", "l2o_dense_destroy", "l2o_dense_theta_count", "l2o_dense_state_floats", "l2o_dense_step",
+    "l2o_dense_unroll_bwd",
     "l2o_launch_count", "l2o_status_string", "l2o_last_cuda_error", "l2o_version",
     "l2o_hrnn_create", "l2o_hrnn_destroy", "l2o_hrnn_theta_count", "l2o_hrnn_state_floats", "l2o_hrnn_coords",
     "l2o_hrnn_workspace_bytes", "l2o_hrnn_init_state", "l2o_hrnn_prepare", "l2o_hrnn_step",
@@ -64,6 +66,21 @@ class BwdArgs(C.Structure):
 class LassoArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("m", C.c_int32), ("n", C.c_int32), ("A", _fp), ("y", _fp), ("x", _fp),
                 ("scale", _fp), ("l1", C.c_float), ("g", _fp), ("f", _fp)]
+
+
+class DenseDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("hidden", C.c_int32 * 2), ("n_in", C.c_int32), ("preprocess", C.c_int32),
+                ("logsign_k", C.c_float), ("n_out", C.c_int32), ("scale", C.c_float), ("tanh_output", C.c_int32)]
+
+
+class DenseStepArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("theta", _fp), ("in_", _fp), ("state_in", _fp), ("state_out", _fp), ("x", _fp),
+                ("delta", _fp)]
+
+
+class DenseBwdArgs(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("T", C.c_int32), ("theta", _fp), ("in_seq", _fp), ("ckpt", _fp), ("g_rec", _fp),
+                ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp)]
 
 
 class HrnnArgs(C.Structure):
@@ -163,6 +180,17 @@ def lib():
     L.l2o_log_and_sign.restype = C.c_int
     L.l2o_lasso_grad.argtypes = [C.POINTER(LassoArgs), C.c_void_p]
     L.l2o_lasso_grad.restype = C.c_int
+    L.l2o_dense_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DenseDesc)]
+    L.l2o_dense_create.restype = C.c_int
+    L.l2o_dense_destroy.argtypes = [C.c_void_p]
+    L.l2o_dense_destroy.restype = None
+    for name in ("l2o_dense_theta_count", "l2o_dense_state_floats"):
+        getattr(L, name).argtypes = [C.c_void_p]
+        getattr(L, name).restype = C.c_int64
+    L.l2o_dense_step.argtypes = [C.c_void_p, C.POINTER(DenseStepArgs), C.c_void_p]
+    L.l2o_dense_step.restype = C.c_int
+    L.l2o_dense_unroll_bwd.argtypes = [C.c_void_p, C.POINTER(DenseBwdArgs), C.c_void_p]
+    L.l2o_dense_unroll_bwd.restype = C.c_int
     L.l2o_launch_count.argtypes = []
     L.l2o_launch_count.restype = C.c_int64
     L.l2o_hrnn_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32]

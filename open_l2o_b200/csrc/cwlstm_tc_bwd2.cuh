@@ -51,6 +51,16 @@ constexpr int kYZ16 = 48, kX2H2P = 20, kX2One = 40, kX1Chunk = 20;
 constexpr uint32_t kLBO16 = 1024, kSBO16 = 2048;
 constexpr int kY16Elems = 128 * 128;           // 32 KB per hi / lo buffer
 
+#ifdef L2O_TC_PROF2
+// timeline instrumentation (scripts/tc_bwd2_prof.cu only): clock64 stamps of CTA 0; role 0 = layer-2 worker (warp 0 lane 0),
+// 1 = layer-1 worker (warp 8 lane 0), 2 = issuer (event id in the low 3 bits)
+__device__ long long g_prof2[3 * 4096];
+#define L2O_PROF2(role, idx, tag) \
+  do { if (blockIdx.x == 0 && (idx) < 4096) g_prof2[(role) * 4096 + (idx)] = (clock64() << 3) | (tag); } while (0)
+#else
+#define L2O_PROF2(role, idx, tag) do { } while (0)
+#endif
+
 struct SmemB2 {
   uint16_t y2h[kY16Elems];     // 1024-B aligned (first member)
   uint16_t y2l[kY16Elems];
@@ -250,6 +260,9 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
   const float inv_nt = imit ? 1.0f / (float)a.n_total : 0.f;
   uint32_t pz = 0, px = 0, pw = 0;
   bool have_prev = false;
+  int pi = 0;
+  const bool prof = (HALF == 0 && q == 0 && lane == 0);
+  (void)pi; (void)prof;
   float acc_wo[kNU], acc_bo = 0.f;
 #pragma unroll
   for (int k = 0; k < kNU; ++k) acc_wo[k] = 0.f;
@@ -269,6 +282,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
       const float* ck = a.ckpt + (int64_t)t * slot;
       // ---- P0: checkpoint rows (h1n(t) IS the checkpointed h1 of slot t+1), A2 = [0 | 0..1..0 | h1n | h2p] --------
       float c2p[kNU];
+      if (prof) { L2O_PROF2(0, pi, 0); ++pi; }
       {
         float h1n[kNU], h2p[kNU];
 #pragma unroll
@@ -290,6 +304,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
           tc_fence_after();
           if (t != T - 1) ld10<HALF>(tX, kA2H2P + U0, dh2c);
         }
+        if (prof) { L2O_PROF2(0, pi, 1); ++pi; }
         if (t == T - 1) {
 #pragma unroll
           for (int k = 0; k < kNU; ++k) dh2c[k] = 0.f;
@@ -308,12 +323,14 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready[0]);
+      if (prof) { L2O_PROF2(0, pi, 2); ++pi; }
       // ---- layer-2 gates, output layer, layer-2 backward: dZ2 -> TMEM (hi in place, lo over A2) -------------------
       const float dy = rt.scale * lam;
       if (HALF == 1) acc_bo += dy;
       mbar_wait(&S.z_done[0], pz);
       pz ^= 1;
       tc_fence_after();
+      if (prof) { L2O_PROF2(0, pi, 3); ++pi; }
       chunks10<HALF>([&](auto k0c, auto ncc) {
         L2O_CHUNK(K0, NC, k0c, ncc);
         float z[4 * NC], hn[NC], dh[NC];
@@ -329,11 +346,13 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.dz_ready[0]);
+      if (prof) { L2O_PROF2(0, pi, 4); ++pi; }
       // ---- staging for dW2^T (in the shadow of the dX2 round trip) ----------------------------------------------------
       if (have_prev) {  // the previous step's dW2 MMAs have drained: Y2 may be overwritten
         mbar_wait(&S.w_done[0], pw);
         pw ^= 1;
       }
+      if (prof) { L2O_PROF2(0, pi, 5); ++pi; }
       stage_dz<HALF>(tZ, yh, yl, c);
       {
         float h1n[kNU], h2p[kNU];
@@ -349,6 +368,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&S.y_ready[0]);
+      if (prof) { L2O_PROF2(0, pi, 6); ++pi; }
       have_prev = true;
       if (act && !imit) lam += a.g_rec[(int64_t)t * n + i];
     }
@@ -410,6 +430,9 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
   const int64_t n = a.n, slot = n * C::SF, ntiles = (n + 127) / 128;
   uint32_t pz = 0, px = 0, pw = 0, px2 = 0;
   bool have_prev = false;
+  int pi = 0;
+  const bool prof = (HALF == 0 && q == 0 && lane == 0);
+  (void)pi; (void)prof;
   if (HALF == 0) {
 #pragma unroll
     for (int k = 0; k < 32 / 4; ++k) tmem_st4(tl + cW1 + 4 * k, 0.f, 0.f, 0.f, 0.f);
@@ -426,6 +449,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
       // ---- P0: A1 = [h1p | u, 1] -----------------------------------------------------------------------------------------
       float c1p[kNU];
       float u4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (prof) { L2O_PROF2(1, pi, 0); ++pi; }
       {
         float h1p[kNU];
 #pragma unroll
@@ -454,6 +478,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
           tc_fence_after();
           if (t != T - 1) ld10<HALF>(tX, U0, dh1);
         }
+        if (prof) { L2O_PROF2(1, pi, 1); ++pi; }
         if (t == T - 1) {
 #pragma unroll
           for (int k = 0; k < kNU; ++k) dh1[k] = 0.f;
@@ -464,6 +489,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready[1]);
+      if (prof) { L2O_PROF2(1, pi, 2); ++pi; }
       // ---- dh1 += dX2(t)[h1n]  (layer 2 has finished step t) -----------------------------------------------------------
       mbar_wait(&S.x_done[0], px2);
       px2 ^= 1;
@@ -476,10 +502,12 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
       }
       tc_fence_before();
       mbar_arrive(&S.x2_taken);
+      if (prof) { L2O_PROF2(1, pi, 3); ++pi; }
       // ---- layer-1 gates + backward ----------------------------------------------------------------------------------------
       mbar_wait(&S.z_done[1], pz);
       pz ^= 1;
       tc_fence_after();
+      if (prof) { L2O_PROF2(1, pi, 4); ++pi; }
       chunks10<HALF>([&](auto k0c, auto ncc) {
         L2O_CHUNK(K0, NC, k0c, ncc);
         float z[4 * NC];
@@ -491,11 +519,13 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.dz_ready[1]);
+      if (prof) { L2O_PROF2(1, pi, 5); ++pi; }
       // ---- staging for dW1^T ---------------------------------------------------------------------------------------------------
       if (have_prev) {
         mbar_wait(&S.w_done[1], pw);
         pw ^= 1;
       }
+      if (prof) { L2O_PROF2(1, pi, 6); ++pi; }
       stage_dz<HALF>(tZ, yh, yl, c);
       {
         float h1p[kNU];
@@ -508,6 +538,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&S.y_ready[1]);
+      if (prof) { L2O_PROF2(1, pi, 7); ++pi; }
       have_prev = true;
     }
   }
@@ -626,6 +657,8 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
     int nA[2] = {0, 0}, nD[2] = {0, 0}, nY[2] = {0, 0}, nW[2] = {0, 0};       // events handled / dW batches finished
     uint32_t pA[2] = {0, 0}, pD[2] = {0, 0}, pY[2] = {0, 0}, pT = 0;
     int dw_left[2] = {0, 0};                          // K-steps of the current dW batch still to issue
+    int pi = 0;
+    (void)pi;
     while (nW[0] < total || nW[1] < total) {
       bool busy = false;
 #pragma unroll
@@ -654,6 +687,7 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
             tc_commit(&S.z_done[l]);
           }
           __syncwarp();
+          L2O_PROF2(2, pi, l == 0 ? 0 : 1); ++pi;
           busy = true;
         }
         // DZ(t): dX_l = dZ_l . W_l^T   (layer 2: only after layer 1 has taken dX2 of the previous step)
@@ -682,6 +716,7 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
             tc_commit(&S.x_done[l]);
           }
           __syncwarp();
+          L2O_PROF2(2, pi, l == 0 ? 2 : 3); ++pi;
           busy = true;
         }
         // Y(t): operands of dW_l^T staged
@@ -707,7 +742,7 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
             if (dw_left[l] == 1) tc_commit(&S.w_done[l]);
           }
           __syncwarp();
-          if (--dw_left[l] == 0) ++nW[l];
+          if (--dw_left[l] == 0) { ++nW[l]; L2O_PROF2(2, pi, l == 0 ? 4 : 5); ++pi; }
         };
         if (dw_left[0] > 0 && (dw_left[1] == 0 || nW[0] <= nW[1])) feed(IC<0>{});
         else if (dw_left[1] > 0) feed(IC<1>{});

@@ -72,6 +72,10 @@ class NetHandle:
         except Exception:
             pass
 
+    def state_size(self, n: int) -> int:
+        """Floats of one state arena for n coordinates."""
+        return self.state_floats * n
+
     def workspace_bytes(self, n: int, T: int):
         """(forward, backward) caller-owned buffer bytes for n coordinates and a T-step unroll."""
         f, b = C.c_size_t(), C.c_size_t()
@@ -143,6 +147,88 @@ class NetHandle:
         a.dtheta = _ptr(dtheta, torch.float64, "dtheta")
         a.delta_seq = _ptr(delta_seq, name="delta_seq")
         _lib.check(_lib.lib().l2o_unroll_bwd(self._h, C.byref(a), _stream()), "l2o_unroll_bwd")
+
+
+class DenseNetHandle:
+    """Row-wise dense LSTM net with run-time shapes (StandardDeepLSTM with output_size > 1 = the reference's
+    KernelDeepLSTM, DM/networks.py:154-236,303-351).  A variable of n = K * R elements in [kw, kh, cin, cout] order is
+    R rows of K inputs (element (k, r) at k * R + r); state per ROW.  Same method surface as NetHandle where the
+    meta-optimizer needs it (step / unroll_bwd / new_state / state_size)."""
+
+    n_in = 1   # one gradient input per element (the RNNProp branches of the executor key on n_in == 2)
+
+    def __init__(self, layers: Sequence[int], k_in: int, k_out: int, preprocess_name: str = "identity",
+                 preprocess_options: Optional[dict] = None, scale: float = 1.0, tanh_output: bool = False):
+        layers = tuple(int(h) for h in layers)
+        if len(layers) > 2:
+            raise L2OError("at most two LSTM layers are supported")
+        if preprocess_name not in ("identity", "LogAndSign"):
+            raise L2OError(f"unsupported preprocess_name {preprocess_name!r} for a dense net")
+        d = _lib.DenseDesc()
+        d.n_layers = len(layers)
+        d.hidden[0] = layers[0] if len(layers) > 0 else 0
+        d.hidden[1] = layers[1] if len(layers) > 1 else 0
+        d.n_in, d.n_out = int(k_in), int(k_out)
+        d.preprocess = _PRE[preprocess_name]
+        d.logsign_k = float((preprocess_options or {}).get("k", 0.0))
+        d.scale, d.tanh_output = float(scale), 1 if tanh_output else 0
+        self.layers, self.k_in, self.k_out = layers, int(k_in), int(k_out)
+        self._h = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.l2o_dense_create(C.byref(self._h), C.byref(d)),
+                   f"l2o_dense_create(layers={layers}, k_in={k_in}, k_out={k_out}, preprocess={preprocess_name})")
+        self.n_theta = int(L.l2o_dense_theta_count(self._h))
+        self.state_floats = int(L.l2o_dense_state_floats(self._h))   # per ROW
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().l2o_dense_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def rows(self, n: int) -> int:
+        if n % self.k_in:
+            raise L2OError(f"{n} elements are not a whole number of rows of {self.k_in}")
+        return n // self.k_in
+
+    def state_size(self, n: int) -> int:
+        return self.state_floats * self.rows(n)
+
+    def new_state(self, n: int, device) -> torch.Tensor:
+        return torch.zeros(max(self.state_size(n), 1), dtype=torch.float32, device=device)
+
+    def state_views(self, arena: torch.Tensor, n: int):
+        out, off, r = [], 0, self.rows(n)
+        for h in self.layers:
+            out.append((arena[off:off + r * h].view(r, h), arena[off + r * h:off + 2 * r * h].view(r, h)))
+            off += 2 * r * h
+        return tuple(out)
+
+    def set_engine(self, engine: int):
+        if engine == ENGINE_TC:
+            raise L2OError("dense nets run on the CUDA-core engine only")
+
+    def step(self, theta, in0, state_in, state_out, *, x=None, delta=None, **unused):
+        a = _lib.DenseStepArgs()
+        a.rows = self.rows(in0.numel())
+        a.theta, a.in_ = _ptr(theta, name="theta"), _ptr(in0, name="in0")
+        a.state_in, a.state_out = _ptr(state_in, name="state_in"), _ptr(state_out, name="state_out")
+        a.x, a.delta = _ptr(x, name="x"), _ptr(delta, name="delta")
+        if theta.numel() != self.n_theta:
+            raise L2OError(f"theta has {theta.numel()} elements, net needs {self.n_theta}")
+        _lib.check(_lib.lib().l2o_dense_step(self._h, C.byref(a), _stream()), "l2o_dense_step")
+
+    def unroll_bwd(self, theta, n, T, in_seq, ckpt, dtheta, *, g_rec=None, labels=None, n_total=0, delta_seq=None):
+        a = _lib.DenseBwdArgs()
+        a.rows, a.T = self.rows(n), T
+        a.theta = _ptr(theta, name="theta")
+        a.in_seq, a.ckpt = _ptr(in_seq, name="in_seq"), _ptr(ckpt, name="ckpt")
+        a.g_rec, a.labels = _ptr(g_rec, name="g_rec"), _ptr(labels, name="labels")
+        a.n_total = n_total
+        a.dtheta = _ptr(dtheta, torch.float64, "dtheta")
+        _lib.check(_lib.lib().l2o_dense_unroll_bwd(self._h, C.byref(a), _stream()), "l2o_dense_unroll_bwd")
 
 
 def adam_step(theta, dtheta, m, v, k: int, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):

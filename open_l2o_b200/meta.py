@@ -172,7 +172,7 @@ class _Program(object):
             for j in subset:
                 n = int(np.prod(self.variables[j]["shape"])) if self.variables[j]["shape"] else 1
                 o = self.var_off[j]
-                if cur is not None and cur.off + cur.n == o:
+                if cur is not None and cur.off + cur.n == o and not getattr(self.nets[key], "per_variable", False):
                     cur.n += n
                 else:
                     cur = _Run(key, self.nets[key], o, n)
@@ -208,9 +208,8 @@ class _Program(object):
     def _alloc_workspaces(self):
         T = self.T
         for r in self.runs:
-            sf = r.net.handle.state_floats
             r.state = r.net.handle.new_state(r.n, self.device)
-            r.ckpt = torch.zeros((T + 1) * max(sf * r.n, 1), device=self.device)
+            r.ckpt = torch.zeros((T + 1) * max(r.net.handle.state_size(r.n), 1), device=self.device)
             r.g_rec = torch.zeros(T + 1, r.n, device=self.device)
             r.x_work = torch.zeros(r.n, device=self.device)
             if r.net.handle.n_in == 2:
@@ -337,7 +336,7 @@ class _Program(object):
         r, T, f = self.runs[0], self.T, self.fused
         h = r.net.handle
         r.x_work.copy_(self.X)
-        state = r.ckpt[:max(h.state_floats * r.n, 1)]
+        state = r.ckpt[:max(h.state_size(r.n), 1)]
         work_state = r.state.clone()
         self.fx_buf.zero_()
         kw = {}
@@ -359,8 +358,7 @@ class _Program(object):
         Xw = self.X.clone()
         fxs = []
         for r in self.runs:
-            sf = r.net.handle.state_floats
-            r.ckpt[:max(sf * r.n, 1)].copy_(r.state)
+            r.ckpt[:max(r.net.handle.state_size(r.n), 1)].copy_(r.state)
             if r.net.handle.n_in == 2:
                 r.m_work.copy_(r.m)
                 r.v_work.copy_(r.v)
@@ -369,7 +367,7 @@ class _Program(object):
             fxs.append(fx)
             for r in self.runs:
                 h = r.net.handle
-                slot = max(h.state_floats * r.n, 1)
+                slot = max(h.state_size(r.n), 1)
                 r.g_rec[t].copy_(g[r.off:r.off + r.n])
                 kw = {}
                 if h.n_in == 2:
@@ -389,7 +387,7 @@ class _Program(object):
                     fx = self._loss_at(Xw)
         fxs.append(fx)
         for r in self.runs:
-            slot = max(r.net.handle.state_floats * r.n, 1)
+            slot = max(r.net.handle.state_size(r.n), 1)
             r.state_final = r.ckpt[T * slot:(T + 1) * slot]
             r.x_work = Xw[r.off:r.off + r.n]
         self._Xw = Xw
@@ -535,9 +533,10 @@ class _MtTask(object):
                 raise NotImplementedError("imitation tasks need each net's variables contiguous in the arena")
             r = runs[0]
             h = r.net.handle
-            sf = h.state_floats
+            if getattr(r.net, "per_variable", False):
+                raise NotImplementedError("imitation tasks are implemented for the coordinate-wise nets")
             sb = dict(run=r, n=r.n, state=h.new_state(r.n, prog.device),
-                      ckpt=torch.zeros((T + 1) * max(sf * r.n, 1), device=prog.device),
+                      ckpt=torch.zeros((T + 1) * max(h.state_size(r.n), 1), device=prog.device),
                       dseq=torch.zeros(T * r.n, device=prog.device),
                       inp=Placeholder("mt{}_input_subset{}".format(index, len(self.subsets))),
                       lab=Placeholder("mt{}_label_subset{}".format(index, len(self.subsets))))

@@ -227,8 +227,90 @@ class RNNprop(StandardDeepLSTM):
 
 
 class KernelDeepLSTM(Network):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("KernelDeepLSTM is outside the accelerated hot path (SURVEY.md 8(f) row 3)")
+    """``DeepLSTM`` for convolutional filters (DM/networks.py:303-351): the input is a filter bank
+    [kernel_w, kernel_h, n_input_channels, n_output_channels]; every (input, output) channel pair is one ROW whose
+    kernel_w*kernel_h entries are the LSTM's inputs, and the output Linear produces the row's kernel_w*kernel_h updates.
+    Runs on the run-time-shaped dense engine (``l2o_dense_*``)."""
+
+    per_variable = True   # one run per optimizee variable (rows differ per filter bank)
+
+    def __init__(self, kernel_shape, layers, preprocess_name="identity", preprocess_options=None, scale=1.0,
+                 initializer=None, name="kernel_deep_lstm", tanh_output=False, seed=0, device=None):
+        self.name = name
+        self._kernel_shape = list(kernel_shape)
+        self._k = int(np.prod(kernel_shape))
+        self._layers = tuple(int(h) for h in layers)
+        self._preprocess_name = preprocess_name
+        self._preprocess_options = dict(preprocess_options or {})
+        self._handle = _engine.DenseNetHandle(self._layers, self._k, self._k, preprocess_name=preprocess_name,
+                                              preprocess_options=self._preprocess_options, scale=scale,
+                                              tanh_output=tanh_output)
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        gen = torch.Generator().manual_seed(seed)
+        parts = []
+        for mod, var, shp in self.variable_shapes():
+            init = _lookup_initializer(initializer, mod, var)
+            if init is not None:
+                t = _convert_initializer(init, shp, gen)
+            elif mod.startswith("lstm"):     # Sonnet 1.x LSTM default: TruncatedNormal(1/sqrt(fan_in)) for w and b
+                fan_in = [s_ for m, v, s_ in self.variable_shapes() if m == mod and v == "w_gates"][0][0]
+                t = _trunc_normal(shp, 1.0 / math.sqrt(fan_in), gen)
+            elif var == "w":                 # Sonnet Linear default
+                t = _trunc_normal(shp, 1.0 / math.sqrt(shp[0]), gen)
+            else:
+                t = torch.zeros(shp)
+            parts.append(t.reshape(-1))
+        self.theta = torch.cat(parts).to(self.device).contiguous()
+        assert self.theta.numel() == self._handle.n_theta
+
+    @property
+    def handle(self):
+        return self._handle
+
+    @property
+    def feat(self):
+        return 2 * self._k if self._preprocess_name == "LogAndSign" else self._k
+
+    def variable_shapes(self):
+        out, k = [], self.feat
+        for i, h in enumerate(self._layers, start=1):
+            out += [("lstm_{}".format(i), "w_gates", (k + h, 4 * h)), ("lstm_{}".format(i), "b_gates", (4 * h,))]
+            k = h
+        out += [("linear", "w", (k, self._k)), ("linear", "b", (self._k,))]
+        return out
+
+    get_variables = StandardDeepLSTM.get_variables
+    set_variables = StandardDeepLSTM.set_variables
+
+    def _check(self, inputs):
+        if inputs.dim() != 4 or list(inputs.shape[:2]) != self._kernel_shape:
+            raise ValueError("KernelDeepLSTM expects a [kw, kh, cin, cout] tensor with kernel shape {}; got {}".format(
+                self._kernel_shape, list(inputs.shape)))
+
+    def initial_state_for_inputs(self, inputs, **kwargs):
+        """Batch size = n_input_channels * n_output_channels (DM/networks.py:347-351)."""
+        self._check(inputs)
+        n = inputs.numel()
+        arena = self._handle.new_state(n, self.theta.device)
+        st = State(self._handle.state_views(arena, n))
+        st.arena = arena
+        return st
+
+    def __call__(self, inputs, prev_state):
+        """update, next_state = net(filter_gradient, prev_state) (DM/networks.py:329-346)."""
+        self._check(inputs)
+        flat = inputs.contiguous().reshape(-1)     # element (k, r) at k * R + r: the transposes are index arithmetic
+        n = flat.numel()
+        arena_in = getattr(prev_state, "arena", None)
+        if arena_in is None:
+            arena_in = torch.cat([t.reshape(-1) for hc in prev_state for t in hc]).contiguous()
+        arena_out = torch.empty_like(arena_in)
+        delta = torch.empty(n, dtype=torch.float32, device=flat.device)
+        self._handle.step(self.theta, flat, arena_in, arena_out, delta=delta)
+        st = State(self._handle.state_views(arena_out, n))
+        st.arena = arena_out
+        return delta.reshape(inputs.shape), st
 
 
 class Sgd(Network):

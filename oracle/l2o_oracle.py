@@ -358,3 +358,41 @@ class MetaTrainerOracle:
         self.mv = tuple(t.detach() for t in res.mv_final) if res.mv_final is not None else None
         self.unroll_idx += 1
         return res
+
+
+# --------------------------------------------------------------------------- KernelDeepLSTM (DM/networks.py:303-351)
+def kernel_net_shapes(kernel_shape, layers, logsign: bool):
+    k = int(np.prod(kernel_shape))
+    out, kin = [], (2 * k if logsign else k)
+    for i, h in enumerate(layers, start=1):
+        out += [(f"lstm_{i}", "w_gates", (kin + h, 4 * h)), (f"lstm_{i}", "b_gates", (4 * h,))]
+        kin = h
+    out += [("linear", "w", (kin, k)), ("linear", "b", (k,))]
+    return out
+
+
+def kernel_net_apply(kernel_shape, layers, theta, inputs, state, preprocess_k=None, scale=1.0, tanh_output=False):
+    """KernelDeepLSTM._build: inputs [kw, kh, cin, cout] -> transpose [cin, cout, kw, kh] -> rows [cin*cout, kw*kh]
+    (DM/networks.py:325-327) -> StandardDeepLSTM._build (preprocess on the expanded last axis, reshape, DeepRNN, Linear
+    with output_size kw*kh, scale; DM/networks.py:207-232) -> transpose back (DM/networks.py:343-346)."""
+    shapes = kernel_net_shapes(kernel_shape, layers, preprocess_k is not None)
+    w, off = {}, 0
+    for mod, var, shp in shapes:
+        n = int(np.prod(shp))
+        w.setdefault(mod, {})[var] = theta[off:off + n].reshape(shp)
+        off += n
+    k = int(np.prod(kernel_shape))
+    rows = inputs.permute(2, 3, 0, 1).reshape(-1, k)
+    if preprocess_k is not None:
+        u = log_and_sign(rows.unsqueeze(-1), preprocess_k).reshape(rows.shape[0], -1)
+    else:
+        u = rows
+    out, nxt = u, []
+    for li, _ in enumerate(layers, start=1):
+        h, c = state[li - 1]
+        hn, cn = lstm_cell(out, h, c, w[f"lstm_{li}"]["w_gates"], w[f"lstm_{li}"]["b_gates"])
+        nxt.append((hn, cn))
+        out = hn
+    y = out @ w["linear"]["w"] + w["linear"]["b"]
+    y = torch.tanh(y) * scale if tanh_output else y * scale
+    return y.t().reshape(inputs.shape), tuple(nxt)

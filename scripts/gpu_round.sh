@@ -27,10 +27,13 @@ if [ $strc -ne 0 ]; then
   echo "staged l2o_step failed: rest of this visit runs with L2O_STEP_STAGE=0"
   export L2O_STEP_STAGE=0
 fi
+# 2c. BPTT v2 timeline
+timeout 120 build/bin/tc_bwd2_prof > $out/${tag}_bwd2_prof.txt 2>&1; echo "prof rc=$?" >> $out/${tag}_bwd2_prof.txt
+cat $out/${tag}_bwd2_prof.txt
 # 3. full GPU suite
-timeout 1500 python -m pytest tests -m gpu -x -q --durations=15 > $out/${tag}_pytest.log 2>&1
+timeout 1500 python -m pytest tests -m gpu --maxfail=10 -q --durations=15 --timeout 400 > $out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest.log
-tail -30 $out/${tag}_pytest.log
+grep -E 'passed|failed|FAILED|ERROR' $out/${tag}_pytest.log | tail -30
 # 4. benches
 timeout 600 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 echo "bench rc=$?"
