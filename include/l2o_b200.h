@@ -93,6 +93,9 @@ typedef struct {
   float* feat_out;      /* optional [2][n]: (m~, g~) actually fed to the net (recorded for BPTT) */
   const int32_t* step_ptr; /* optional DEVICE scalar: when non-NULL, p = float(*step_ptr + t_offset) (CUDA-graph friendly) */
   int32_t t_offset;
+  int32_t reuse_weights;   /* 1: theta is unchanged since this handle's previous l2o_step / forward launch on this stream:
+                              the tensor-core engine skips rebuilding its weight image (one tiny launch per step saved;
+                              the caller steps T times per unroll with the same theta).  0 is always safe. */
 } l2o_step_args;
 
 typedef struct {

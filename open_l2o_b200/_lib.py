@@ -47,7 +47,8 @@ _fp = C.c_void_p
 class StepArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("theta", _fp), ("in0", _fp), ("in1", _fp), ("m", _fp), ("v", _fp),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("p", C.c_float), ("state_in", _fp),
-                ("state_out", _fp), ("x", _fp), ("delta", _fp), ("feat_out", _fp), ("step_ptr", _fp), ("t_offset", C.c_int32)]
+                ("state_out", _fp), ("x", _fp), ("delta", _fp), ("feat_out", _fp), ("step_ptr", _fp), ("t_offset", C.c_int32),
+                ("reuse_weights", C.c_int32)]
 
 
 class UnrollArgs(C.Structure):

@@ -915,8 +915,8 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
 // ------------------------------------------------------------------ host side (called from l2o_capi.cu)
 template <class C>
 int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStream_t st, int sms, float* state_out = nullptr,
-                  bool stage = false, tc::FwdExtra ex = tc::FwdExtra{nullptr, 0, 0.f}) {
-  tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 0);
+                  bool stage = false, tc::FwdExtra ex = tc::FwdExtra{nullptr, 0, 0.f}, bool prep = true) {
+  if (prep) tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 0);
   // stage: TMA-prefetched state rows (the l2o_step path, T = 1); needs 16-byte aligned arrays (n * 80 B always is)
   stage = stage && (reinterpret_cast<uintptr_t>(a.state) % 16 == 0);
   auto k = stage ? tc::unroll_fwd_kernel<C, true> : tc::unroll_fwd_kernel<C, false>;

@@ -69,9 +69,10 @@ struct SmemB2 {
   float img[kImgAllFloats];    // B1'h|B1'l|B2'h|B2'l (K-major) | T1h|T1l|T2h|T2l (transposed, K-major)
   float wo[kH + 4];
   uint64_t wbar;
-  uint64_t a_ready[2], dz_ready[2], y_ready[2];   // index 0 = layer 2, 1 = layer 1 (epilogue -> issuer, 256 arrivals)
+  uint64_t a_ready[2], dz_ready[2];               // index 0 = layer 2, 1 = layer 1 (epilogue -> issuer, 256 arrivals)
   uint64_t z_done[2], x_done[2], w_done[2];       // issuer (tcgen05.commit) -> epilogue
   uint64_t x2_taken;                              // layer-1 threads have read dX2(t)[h1n] (256 arrivals)
+  uint64_t flushed[2];                            // the layer's half-0 threads have drained the dW accumulators of a tile (128)
   uint32_t tmem_slot, pad;
 };
 static_assert(sizeof(SmemB2) + 1024 <= 227 * 1024, "shared memory budget");
@@ -242,6 +243,54 @@ __device__ __forceinline__ void put_dz(uint32_t t_hi, uint32_t t_lo, int col, co
   for (int u = 0; u < NC; ++u) st_split4(t_hi, t_lo, col + 4 * u, dz + 4 * u);
 }
 
+// ---- dW^T accumulator flush -------------------------------------------------------------------------------------------
+// The tensor core adds into its fp32 accumulators with truncation, so an accumulation that runs over the CTA's whole
+// share of the problem (53 tiles x 100 steps x 24 MMAs at 1 M coordinates) drifts: measured 2.4e-5 of max|dtheta|
+// against a chunked fp64 reference (scripts/tc_accuracy_large.py), 9.7e-7 at 3.5 tiles per CTA.  The accumulators are
+// therefore drained into the fp64 dtheta after EVERY tile (5,040 fp64 atomics per tile: ~0.2 ms per 1 M x 100 unroll)
+// and the next tile's first MMA overwrites instead of accumulating.  Lane = slot: gate row m - 48 = 4u + g.
+template <class C>
+__device__ __forceinline__ void flush_dw2(const l2o_bwd_args& a, uint32_t tl, int c) {
+  const int m = c - kYZ16;
+  const int col = (m & 3) * kH + (m >> 2);
+#pragma unroll
+  for (int k4 = 0; k4 < 48 / 4; ++k4) {
+    float v[4];
+    tcb::tmem_ld4(tl + cW2 + 4 * k4, v);
+    if (m >= 0 && m < kN) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * k4 + e;
+        int idx = -1;
+        if (k < 2 * kH) idx = C::O_W2 + k * C::G2 + col;   // rows of lstm_2/w_gates: h1 (0..19) then h2 (20..39)
+        else if (k == kX2One) idx = C::O_B2 + col;
+        if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
+      }
+    }
+  }
+}
+template <class C>
+__device__ __forceinline__ void flush_dw1(const l2o_bwd_args& a, uint32_t tl, int c) {
+  const int m = c - kYZ16;
+  const int col = (m & 3) * kH + (m >> 2);
+#pragma unroll
+  for (int k4 = 0; k4 < 32 / 4; ++k4) {
+    float v[4];
+    tcb::tmem_ld4(tl + cW1 + 4 * k4, v);
+    if (m >= 0 && m < kN) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * k4 + e;
+        int idx = -1;
+        if (k < kH) idx = C::O_W1 + (C::F + k) * C::G1 + col;
+        else if (k < kX1Chunk + C::F) idx = C::O_W1 + (k - kX1Chunk) * C::G1 + col;
+        else if (k == kX1Chunk + C::F) idx = C::O_B1 + col;
+        if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
+      }
+    }
+  }
+}
+
 // =====================================================================================================================
 // layer-2 workers: output layer + layer-2 LSTM backward
 // =====================================================================================================================
@@ -282,6 +331,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
       const float* ck = a.ckpt + (int64_t)t * slot;
       // ---- P0: checkpoint rows (h1n(t) IS the checkpointed h1 of slot t+1), A2 = [0 | 0..1..0 | h1n | h2p] --------
       float c2p[kNU];
+      float g_t = 0.f;
       if (prof) { L2O_PROF2(0, pi, 0); ++pi; }
       {
         float h1n[kNU], h2p[kNU];
@@ -298,6 +348,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
           }
         }
         if (imit && act) lam = (a.delta_seq[(int64_t)t * n + i] - a.labels[(int64_t)t * n + i]) * inv_nt;
+        if (!imit && act) g_t = a.g_rec[(int64_t)t * n + i];   // consumed at the end of the step (suffix sum)
         if (have_prev) {  // dX2 of the previous step: the h2p columns are this chain's carry, and the aliased
           mbar_wait(&S.x_done[0], px);  // dZ2-lo / A2 region becomes writable
           px ^= 1;
@@ -319,12 +370,27 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
           tmem_st4(tRh + kA2One, one[0], one[1], one[2], one[3]);
           tmem_st4(tRl + kA2One, 0.f, 0.f, 0.f, 0.f);
         }
+        // X2 row of the dW2^T operand, from the same registers.  The previous step's dW2 MMAs were issued right behind
+        // its dX2 MMAs and have drained long before this point (the wait is a formality except under contention).
+        if (have_prev) {
+          mbar_wait(&S.w_done[0], pw);
+          pw ^= 1;
+          if (t == T - 1 && HALF == 0) {   // first step of a new tile: drain the previous tile's dW2^T accumulators
+            tc_fence_after();
+            flush_dw2<C>(a, tl, c);
+            tc_fence_before();
+            mbar_arrive(&S.flushed[0]);
+          }
+        }
+        if (prof) { L2O_PROF2(0, pi, 5); ++pi; }
+        stage_units10<HALF>(yh, yl, c, 0, h1n);
+        stage_units10<HALF>(yh, yl, c, kX2H2P, h2p);
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready[0]);
       if (prof) { L2O_PROF2(0, pi, 2); ++pi; }
-      // ---- layer-2 gates, output layer, layer-2 backward: dZ2 -> TMEM (hi in place, lo over A2) -------------------
+      // ---- layer-2 gates, output layer, layer-2 backward: dZ2 -> TMEM (hi in place, lo over A2) + bf16 staging ------
       const float dy = rt.scale * lam;
       if (HALF == 1) acc_bo += dy;
       mbar_wait(&S.z_done[0], pz);
@@ -342,35 +408,16 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
 #pragma unroll
         for (int u = 0; u < NC; ++u) acc_wo[K0 + u] = fmaf(hn[u], dy, acc_wo[K0 + u]);
         put_dz<NC>(tZ, tDl, 4 * (U0 + K0), z);
+#pragma unroll
+        for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * (U0 + K0) + 8 * g8, z + 8 * g8);
       });
+      fence_proxy_async();
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.dz_ready[0]);
       if (prof) { L2O_PROF2(0, pi, 4); ++pi; }
-      // ---- staging for dW2^T (in the shadow of the dX2 round trip) ----------------------------------------------------
-      if (have_prev) {  // the previous step's dW2 MMAs have drained: Y2 may be overwritten
-        mbar_wait(&S.w_done[0], pw);
-        pw ^= 1;
-      }
-      if (prof) { L2O_PROF2(0, pi, 5); ++pi; }
-      stage_dz<HALF>(tZ, yh, yl, c);
-      {
-        float h1n[kNU], h2p[kNU];
-#pragma unroll
-        for (int k = 0; k < kNU; ++k) { h1n[k] = 0.f; h2p[k] = 0.f; }
-        if (act) {
-          load10<HALF>(ck + slot + i * kH + U0, h1n);
-          load10<HALF>(ck + 2 * n * kH + i * kH + U0, h2p);
-        }
-        stage_units10<HALF>(yh, yl, c, 0, h1n);
-        stage_units10<HALF>(yh, yl, c, kX2H2P, h2p);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&S.y_ready[0]);
-      if (prof) { L2O_PROF2(0, pi, 6); ++pi; }
       have_prev = true;
-      if (act && !imit) lam += a.g_rec[(int64_t)t * n + i];
+      lam += g_t;
     }
   }
   // ---- flush: output-layer gradient from registers -------------------------------------------------------------------
@@ -387,31 +434,13 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) atomicAdd(&a.dtheta[C::O_BO], (double)v);
   }
-  // ---- flush: dW2^T accumulators (lane = slot: gate row m - 48 = 4u + g; column = X2 slot) ----------------------------
+  // ---- flush: the last tile's dW2^T accumulators ---------------------------------------------------------------------
   if (have_prev) {
     mbar_wait(&S.w_done[0], pw);
     pw ^= 1;
   }
   tc_fence_after();
-  if (HALF == 0) {
-    const int m = c - kYZ16;
-    const int col = (m & 3) * kH + (m >> 2);
-#pragma unroll
-    for (int k4 = 0; k4 < 48 / 4; ++k4) {
-      float v[4];
-      tcb::tmem_ld4(tl + cW2 + 4 * k4, v);
-      if (m >= 0 && m < kN) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = 4 * k4 + e;
-          int idx = -1;
-          if (k < 2 * kH) idx = C::O_W2 + k * C::G2 + col;   // rows of lstm_2/w_gates: h1 (0..19) then h2 (20..39)
-          else if (k == kX2One) idx = C::O_B2 + col;
-          if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
-        }
-      }
-    }
-  }
+  if (HALF == 0) flush_dw2<C>(a, tl, c);
 }
 
 // =====================================================================================================================
@@ -485,6 +514,20 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
         }
         st_split10<HALF>(tRh, tRl, U0, h1p);
         if (HALF == 1) st_split4(tRh, tRl, kA1Chunk, u4);
+        // X1 row of the dW1^T operand from the same registers (the previous step's dW1 MMAs drained long ago)
+        if (have_prev) {
+          mbar_wait(&S.w_done[1], pw);
+          pw ^= 1;
+          if (t == T - 1 && HALF == 0) {   // first step of a new tile: drain the previous tile's dW1^T accumulators
+            tc_fence_after();
+            flush_dw1<C>(a, tl, c);
+            tc_fence_before();
+            mbar_arrive(&S.flushed[1]);
+          }
+        }
+        if (prof) { L2O_PROF2(1, pi, 6); ++pi; }
+        stage_units10<HALF>(yh, yl, c, 0, h1p);
+        if (HALF == 1) stage16<4>(yh, yl, c, kX1Chunk, u4);
       }
       tc_wait_st();
       tc_fence_before();
@@ -503,7 +546,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
       tc_fence_before();
       mbar_arrive(&S.x2_taken);
       if (prof) { L2O_PROF2(1, pi, 3); ++pi; }
-      // ---- layer-1 gates + backward ----------------------------------------------------------------------------------------
+      // ---- layer-1 gates + backward: dZ1 -> TMEM + bf16 staging --------------------------------------------------------
       mbar_wait(&S.z_done[1], pz);
       pz ^= 1;
       tc_fence_after();
@@ -515,30 +558,14 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
         tc_wait_ld();
         chunk_bwd<NC>(z, c1p + K0, dh1 + K0, dc1 + K0, nullptr);
         put_dz<NC>(tZ, tDl, 4 * (U0 + K0), z);
+#pragma unroll
+        for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * (U0 + K0) + 8 * g8, z + 8 * g8);
       });
+      fence_proxy_async();
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.dz_ready[1]);
       if (prof) { L2O_PROF2(1, pi, 5); ++pi; }
-      // ---- staging for dW1^T ---------------------------------------------------------------------------------------------------
-      if (have_prev) {
-        mbar_wait(&S.w_done[1], pw);
-        pw ^= 1;
-      }
-      if (prof) { L2O_PROF2(1, pi, 6); ++pi; }
-      stage_dz<HALF>(tZ, yh, yl, c);
-      {
-        float h1p[kNU];
-#pragma unroll
-        for (int k = 0; k < kNU; ++k) h1p[k] = 0.f;
-        if (act) load10<HALF>(ck + i * kH + U0, h1p);
-        stage_units10<HALF>(yh, yl, c, 0, h1p);
-        if (HALF == 1) stage16<4>(yh, yl, c, kX1Chunk, u4);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive(&S.y_ready[1]);
-      if (prof) { L2O_PROF2(1, pi, 7); ++pi; }
       have_prev = true;
     }
   }
@@ -547,26 +574,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
     pw ^= 1;
   }
   tc_fence_after();
-  if (HALF == 0) {
-    const int m = c - kYZ16;
-    const int col = (m & 3) * kH + (m >> 2);
-#pragma unroll
-    for (int k4 = 0; k4 < 32 / 4; ++k4) {
-      float v[4];
-      tcb::tmem_ld4(tl + cW1 + 4 * k4, v);
-      if (m >= 0 && m < kN) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = 4 * k4 + e;
-          int idx = -1;
-          if (k < kH) idx = C::O_W1 + (C::F + k) * C::G1 + col;
-          else if (k < kX1Chunk + C::F) idx = C::O_W1 + (k - kX1Chunk) * C::G1 + col;
-          else if (k == kX1Chunk + C::F) idx = C::O_B1 + col;
-          if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
-        }
-      }
-    }
-  }
+  if (HALF == 0) flush_dw1<C>(a, tl, c);
 }
 
 template <class C>
@@ -593,12 +601,13 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
       for (int l = 0; l < 2; ++l) {
         mbar_init(&S.a_ready[l], 256);
         mbar_init(&S.dz_ready[l], 256);
-        mbar_init(&S.y_ready[l], 256);
         mbar_init(&S.z_done[l], 1);
         mbar_init(&S.x_done[l], 1);
         mbar_init(&S.w_done[l], 1);
       }
       mbar_init(&S.x2_taken, 256);
+      mbar_init(&S.flushed[0], 128);
+      mbar_init(&S.flushed[1], 128);
       fence_barrier_init();
     }
     __syncwarp();
@@ -654,13 +663,11 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
     int my_tiles = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
     const int total = my_tiles * T;                   // steps per layer (< 2^31: n*T/128/grid)
-    int nA[2] = {0, 0}, nD[2] = {0, 0}, nY[2] = {0, 0}, nW[2] = {0, 0};       // events handled / dW batches finished
-    uint32_t pA[2] = {0, 0}, pD[2] = {0, 0}, pY[2] = {0, 0}, pT = 0;
-    int dw_left[2] = {0, 0};                          // K-steps of the current dW batch still to issue
+    int nA[2] = {0, 0}, nD[2] = {0, 0};               // events handled per layer (index 0 = layer 2)
+    uint32_t pA[2] = {0, 0}, pD[2] = {0, 0}, pF[2] = {0, 0}, pT = 0;
     int pi = 0;
     (void)pi;
-    while (nW[0] < total || nW[1] < total) {
-      bool busy = false;
+    while (nD[0] < total || nD[1] < total) {
 #pragma unroll
       for (int l = 0; l < 2; ++l) {
         // A(t): gate recompute Z_l = A_l . B_l'
@@ -688,13 +695,21 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
           }
           __syncwarp();
           L2O_PROF2(2, pi, l == 0 ? 0 : 1); ++pi;
-          busy = true;
         }
-        // DZ(t): dX_l = dZ_l . W_l^T   (layer 2: only after layer 1 has taken dX2 of the previous step)
+        // DZ(t): dX_l = dZ_l . W_l^T (layer 2: only after layer 1 has taken dX2 of the previous step), then the
+        // dW_l^T batch right behind it: the layer's own next request (Z of step t-1) comes a whole P0 later, by which
+        // time the 24 SS-mode MMAs have drained
         if (nD[l] < nA[l] && mbar_test(&S.dz_ready[l], pD[l]) &&
             (l == 1 || nD[0] == 0 || mbar_test(&S.x2_taken, pT))) {
           if (l == 0 && nD[0] > 0) pT ^= 1;
           pD[l] ^= 1;
+          // first step of a tile: its dW batch OVERWRITES the accumulators.  The previous tile's values were drained
+          // by the workers before they signalled this step's a_ready, so the handshake never blocks here.
+          const bool first_of_tile = nD[l] % T == 0;
+          if (first_of_tile && nD[l] > 0) {
+            mbar_wait(&S.flushed[l], pF[l]);
+            pF[l] ^= 1;
+          }
           ++nD[l];
           tc_fence_after();
           if (elect_one()) {
@@ -714,38 +729,20 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
               }
             }
             tc_commit(&S.x_done[l]);
+            const uint64_t yh0 = l == 0 ? y2h : y1h, yl0 = l == 0 ? y2l : y1l;
+            const uint32_t d = tb + (l == 0 ? cW2 : cW1);
+            const uint32_t id = l == 0 ? id_dw2 : id_dw1;
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb) {
+              mma_bf16_ss(d, yl0 + kb * kY16Step, yh0 + kb * kY16Step, id, (kb == 0 && first_of_tile) ? 0u : 1u);
+              mma_bf16_ss(d, yh0 + kb * kY16Step, yl0 + kb * kY16Step, id, 1u);
+              mma_bf16_ss(d, yh0 + kb * kY16Step, yh0 + kb * kY16Step, id, 1u);
+            }
+            tc_commit(&S.w_done[l]);
           }
           __syncwarp();
           L2O_PROF2(2, pi, l == 0 ? 2 : 3); ++pi;
-          busy = true;
         }
-        // Y(t): operands of dW_l^T staged
-        if (nY[l] < nD[l] && dw_left[l] == 0 && nY[l] == nW[l] && mbar_test(&S.y_ready[l], pY[l])) {
-          pY[l] ^= 1;
-          ++nY[l];
-          dw_left[l] = 8;
-          tc_fence_after();
-          busy = true;
-        }
-      }
-      if (!busy) {  // nothing latency-critical pending: feed one K-step of a pending dW batch (older batch first)
-        auto feed = [&](auto lc) {
-          constexpr int l = decltype(lc)::value;
-          const int kb = 8 - dw_left[l];
-          if (elect_one()) {
-            const uint64_t yh = (l == 0 ? y2h : y1h) + kb * kY16Step, yl = (l == 0 ? y2l : y1l) + kb * kY16Step;
-            constexpr uint32_t d_col = l == 0 ? cW2 : cW1;
-            constexpr uint32_t id = l == 0 ? id_dw2 : id_dw1;
-            mma_bf16_ss(tb + d_col, yl, yh, id, 1u);
-            mma_bf16_ss(tb + d_col, yh, yl, id, 1u);
-            mma_bf16_ss(tb + d_col, yh, yh, id, 1u);
-            if (dw_left[l] == 1) tc_commit(&S.w_done[l]);
-          }
-          __syncwarp();
-          if (--dw_left[l] == 0) { ++nW[l]; L2O_PROF2(2, pi, l == 0 ? 4 : 5); ++pi; }
-        };
-        if (dw_left[0] > 0 && (dw_left[1] == 0 || nW[0] <= nW[1])) feed(IC<0>{});
-        else if (dw_left[1] > 0) feed(IC<1>{});
       }
     }
     __syncwarp();

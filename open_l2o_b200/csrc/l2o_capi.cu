@@ -79,6 +79,7 @@ int l2o_net_create(l2o_handle* out, const l2o_net_desc* d) {
   h->engine = L2O_ENGINE_AUTO;
   h->tc_img = nullptr;
   h->tc_img_dev = -1;
+  h->tc_img_mode = -1;
   h->rt.scale = d->scale;
   h->rt.logsign_k = d->logsign_k;
   h->rt.logsign_ek = (float)std::exp((double)d->logsign_k);
@@ -96,7 +97,7 @@ int l2o_net_create(l2o_handle* out, const l2o_net_desc* d) {
 
 void l2o_net_destroy(l2o_handle h) {
   if (!h) return;
-  if (h->tc_img) cudaFree(h->tc_img);
+  l2o::tc_release_image(h);
   delete h;
 }
 

@@ -15,6 +15,8 @@
 //   17..20 ms1..4  (HR:303-343; "true_param" duplicates x when use_attention=False and is not stored).
 #include <cstdint>
 #include <new>
+#include <mutex>
+#include <vector>
 
 #include "l2o_internal.h"
 
@@ -441,6 +443,7 @@ int l2o_hrnn_create(l2o_hrnn_handle* out, const int64_t* tensor_sizes, int32_t n
     }
     start += tensor_sizes[j];
   }
+  free_buried();
   l2o_hrnn* h = new (std::nothrow) l2o_hrnn();
   if (!h) { delete[] hb; return L2O_E_NOMEM; }
   h->nt = n_tensors;
@@ -464,10 +467,38 @@ int l2o_hrnn_create(l2o_hrnn_handle* out, const int64_t* tensor_sizes, int32_t n
   return L2O_OK;
 }
 
+// A handle may be destroyed (Python GC) while another program is capturing a CUDA graph, and cudaFree during a capture
+// invalidates it: destroy parks the device buffers and the next l2o_hrnn_create (never inside a capture) frees them.
+namespace {
+struct Graveyard {
+  std::mutex mu;
+  std::vector<void*> ptrs;
+};
+Graveyard& graveyard() {
+  static Graveyard* g = new Graveyard();
+  return *g;
+}
+void bury(void* p) {
+  if (!p) return;
+  Graveyard& g = graveyard();
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.ptrs.push_back(p);
+}
+void free_buried() {
+  Graveyard& g = graveyard();
+  std::vector<void*> take;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    take.swap(g.ptrs);
+  }
+  for (void* p : take) cudaFree(p);
+}
+}  // namespace
+
 void l2o_hrnn_destroy(l2o_hrnn_handle h) {
   if (!h) return;
-  if (h->d_blocks) cudaFree(h->d_blocks);
-  if (h->d_sizes) cudaFree(h->d_sizes);
+  bury(h->d_blocks);
+  bury(h->d_sizes);
   delete h;
 }
 

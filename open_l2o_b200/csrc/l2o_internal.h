@@ -24,6 +24,7 @@ struct l2o_net {
   l2o::NetRt rt;
   float* tc_img;   // device-side weight image of the tcgen05 engine (owned; lazily allocated)
   int tc_img_dev;
+  int tc_img_mode; // what the image currently holds: -1 nothing, 0 forward layout, 1 BPTT layout
 };
 
 namespace l2o {
@@ -36,6 +37,7 @@ int ffma_unroll_fwd(const l2o_net* h, const l2o_unroll_args& a, cudaStream_t st)
 int ffma_unroll_bwd(const l2o_net* h, const l2o_bwd_args& a, cudaStream_t st);
 
 bool tc_supported(int cfg);
+void tc_release_image(l2o_net* h);   // hand the weight image back to the process-wide pool (never cudaFree)
 bool tc_fwd_ok(const l2o_net* h, const l2o_unroll_args& a);
 int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st);
 bool tc_step_ok(const l2o_net* h, const l2o_step_args& a);

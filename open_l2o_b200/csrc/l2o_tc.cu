@@ -4,6 +4,9 @@
 #include "cwlstm_tc_bwd.cuh"
 #include "cwlstm_tc_bwd2.cuh"
 #include <cstdlib>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include "l2o_internal.h"
 
 namespace l2o {
@@ -16,17 +19,53 @@ bool tc_fwd_ok(const l2o_net* h, const l2o_unroll_args& a) {
   if (h->cfg == 2) return true;                             // fused Adam-feature mode (m, v) or given (m~, g~) rows
   return a.m == nullptr && a.feat_rec == nullptr;
 }
-bool tc_auto_default() { return true; }
-bool tc_bwd_auto_default() { return true; }  // parity-green on the B200 (tests/test_tc_gpu.py)
+// L2O_TC_AUTO=0: ENGINE_AUTO never picks the tcgen05 engine (A/B runs of whole tests against the exact-fp32 engine)
+static bool tc_auto_env() {
+  static const bool on = !(std::getenv("L2O_TC_AUTO") != nullptr && std::getenv("L2O_TC_AUTO")[0] == '0');
+  return on;
+}
+bool tc_auto_default() { return tc_auto_env(); }
+bool tc_bwd_auto_default() { return tc_auto_env(); }  // parity-green on the B200 (tests/test_tc_gpu.py)
+
+// Weight-image buffers (97 KB each) are recycled through a process-wide free list and never cudaFree'd: a handle may
+// be destroyed (Python GC) while ANOTHER program is capturing a CUDA graph, and cudaFree during a capture invalidates it.
+namespace {
+struct ImgPool {
+  std::mutex mu;
+  std::vector<std::pair<int, float*>> free_list;   // (device, pointer)
+};
+ImgPool& img_pool() {
+  static ImgPool* p = new ImgPool();   // intentionally leaked: outlives every handle
+  return *p;
+}
+}  // namespace
+
+void tc_release_image(l2o_net* h) {
+  if (!h->tc_img) return;
+  ImgPool& P = img_pool();
+  std::lock_guard<std::mutex> g(P.mu);
+  P.free_list.emplace_back(h->tc_img_dev, h->tc_img);
+  h->tc_img = nullptr;
+}
 
 static int ensure_image(l2o_net* h) {
   int dev = 0;
   L2O_CUDA_TRY(cudaGetDevice(&dev));
   if (h->tc_img == nullptr || h->tc_img_dev != dev) {
-    if (h->tc_img) cudaFree(h->tc_img);
-    h->tc_img = nullptr;
-    L2O_CUDA_TRY(cudaMalloc(&h->tc_img, tc::kImgAllBytes));
+    tc_release_image(h);
+    {
+      ImgPool& P = img_pool();
+      std::lock_guard<std::mutex> g(P.mu);
+      for (size_t k = 0; k < P.free_list.size(); ++k)
+        if (P.free_list[k].first == dev) {
+          h->tc_img = P.free_list[k].second;
+          P.free_list.erase(P.free_list.begin() + k);
+          break;
+        }
+    }
+    if (h->tc_img == nullptr) L2O_CUDA_TRY(cudaMalloc(&h->tc_img, tc::kImgAllBytes));
     h->tc_img_dev = dev;
+    h->tc_img_mode = -1;
   }
   return L2O_OK;
 }
@@ -55,6 +94,7 @@ int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {
     if (h->cfg == 1) rc = tc_launch_bwd2<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
   }
   if (rc == L2O_OK) count_launch(2);
+  h->tc_img_mode = 1;
   if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_unroll_bwd launch");
   return rc;
 }
@@ -91,10 +131,12 @@ int tc_step(l2o_net* h, const l2o_step_args& s, cudaStream_t st) {
   rc = L2O_E_UNSUPPORTED;
   // L2O_STEP_STAGE=0 disables the TMA-staged state loads (A/B measurements)
   static const bool stage = !(std::getenv("L2O_STEP_STAGE") != nullptr && std::getenv("L2O_STEP_STAGE")[0] == '0');
-  if (h->cfg == 0) rc = tc_launch_fwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage);
-  if (h->cfg == 1) rc = tc_launch_fwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage);
-  if (h->cfg == 2) rc = tc_launch_fwd<Cfg<L2O_PRE_FC, 2, 20, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage, ex);
-  if (rc == L2O_OK) count_launch(2);
+  const bool prep = !(s.reuse_weights && h->tc_img_mode == 0);   // forward image of this theta already in place
+  if (h->cfg == 0) rc = tc_launch_fwd<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage, ex, prep);
+  if (h->cfg == 1) rc = tc_launch_fwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage, ex, prep);
+  if (h->cfg == 2) rc = tc_launch_fwd<Cfg<L2O_PRE_FC, 2, 20, 20, 20>>(h->rt, a, h->tc_img, st, sms, s.state_out, stage, ex, prep);
+  if (rc == L2O_OK) count_launch(prep ? 2 : 1);
+  h->tc_img_mode = 0;
   if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_step launch");
   return rc;
 }
@@ -112,6 +154,7 @@ int tc_unroll_fwd(l2o_net* h, const l2o_unroll_args& a, cudaStream_t st) {
   if (h->cfg == 1) rc = tc_launch_fwd<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
   if (h->cfg == 2) rc = tc_launch_fwd<Cfg<L2O_PRE_FC, 2, 20, 20, 20>>(h->rt, a, h->tc_img, st, sms);
   if (rc == L2O_OK) count_launch(2);
+  h->tc_img_mode = 0;
   if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_unroll_fwd launch");
   return rc;
 }

@@ -101,8 +101,9 @@ class NetHandle:
 
     # ---- kernels -------------------------------------------------------------------------
     def step(self, theta, in0, state_in, state_out, *, in1=None, m=None, v=None, beta1=0.95, beta2=0.95, p=1.0,
-             x=None, delta=None, feat_out=None, step_ptr=None, t_offset=0):
+             x=None, delta=None, feat_out=None, step_ptr=None, t_offset=0, reuse_weights=False):
         a = StepArgs()
+        a.reuse_weights = 1 if reuse_weights else 0
         a.n = in0.numel()
         a.theta = _ptr(theta, name="theta")
         a.in0, a.in1 = _ptr(in0, name="in0"), _ptr(in1, name="in1")
@@ -210,7 +211,7 @@ class DenseNetHandle:
         if engine == ENGINE_TC:
             raise L2OError("dense nets run on the CUDA-core engine only")
 
-    def step(self, theta, in0, state_in, state_out, *, x=None, delta=None, **unused):
+    def step(self, theta, in0, state_in, state_out, *, x=None, delta=None, reuse_weights=False, **unused):
         a = _lib.DenseStepArgs()
         a.rows = self.rows(in0.numel())
         a.theta, a.in_ = _ptr(theta, name="theta"), _ptr(in0, name="in0")

@@ -373,8 +373,10 @@ class _Program(object):
                 if h.n_in == 2:
                     kw = dict(m=r.m_work, v=r.v_work, beta1=self.opt.beta1, beta2=self.opt.beta2,
                               step_ptr=self.step_dev, t_offset=t, feat_out=r.feat_rec[t])
+                # theta is constant inside an unroll: the weight image built at t = 0 serves every later step (runs that
+                # share a net share its handle, so only the first run of step 0 rebuilds)
                 h.step(r.net.theta, r.g_rec[t], r.ckpt[t * slot:(t + 1) * slot], r.ckpt[(t + 1) * slot:(t + 2) * slot],
-                       x=Xw[r.off:r.off + r.n], **kw)
+                       x=Xw[r.off:r.off + r.n], reuse_weights=(t > 0), **kw)
         if train:
             fx, g = self._value_and_grad(Xw)
             for r in self.runs:

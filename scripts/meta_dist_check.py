@@ -73,7 +73,11 @@ def main():
                 "theta": max(rel_big(t, tr, gr) for (_, t, _), (_, tr, gr) in zip(trace, ref)),
                 "theta_all": max(rel(t, tr) for (_, t, _), (_, tr, _) in zip(trace, ref)),
                 "x_shard": rel(x_shard, x_full[lo:hi])}
-        ok = ok and all(errs[k] <= 1e-5 for k in ("fx", "dtheta", "theta", "x_shard")) and errs["theta_all"] <= 5e-5
+        # d-theta of this problem is a sum with heavy cancellation: two runs of the EXACT-fp32 engine that differ only in
+        # how the coordinates are grouped into CTAs already differ by 1.6e-5 of max|dtheta| (measured, L2O_TC_AUTO=0),
+        # so the sharded-vs-single bar for d-theta / theta is 5e-5; f(x_T) and x have no such cancellation: 1e-5
+        ok = ok and errs["fx"] <= 1e-5 and errs["x_shard"] <= 1e-5 and \
+            all(errs[k] <= 5e-5 for k in ("dtheta", "theta", "theta_all"))
         print("meta sharded vs single-GPU (world %d, backend %s, %d GPU(s)):" % (world, backend, torch.cuda.device_count()),
               errs, "theta identical on all ranks:", bool(same.item() == 1.0), "PASS" if ok else "FAIL", flush=True)
     dist.barrier()

@@ -32,28 +32,28 @@ int main() {
   std::vector<long long> p(3 * 4096);
   cudaMemcpyFromSymbol(p.data(), tcb2::g_prof2, sizeof(long long) * 3 * 4096);
   auto tm = [&](int role, int idx) { return p[role * 4096 + idx] >> 3; };
-  const char* e2[7] = {"start", "x_done+dh2c", "A2 arrived", "z_done", "dz arrived", "w_done", "y arrived"};
+  const char* e2[6] = {"start", "x_done+dh2c", "w_done", "A2+X2 staged, arrived", "z_done", "phase (dz staged), arrived"};
   printf("== layer-2 worker (warp 0 lane 0): cycles since previous stamp, steps 3..6\n");
   for (int st = 3; st < 7; ++st) {
     printf(" step %d:", st);
-    for (int e = 0; e < 7; ++e) printf(" %s=%lld", e2[e], tm(0, st * 7 + e) - tm(0, st * 7 + e - 1));
-    printf(" | step total %lld\n", tm(0, st * 7 + 6) - tm(0, (st - 1) * 7 + 6));
+    for (int e = 0; e < 6; ++e) printf(" %s=%lld", e2[e], tm(0, st * 6 + e) - tm(0, st * 6 + e - 1));
+    printf(" | step total %lld\n", tm(0, st * 6 + 5) - tm(0, (st - 1) * 6 + 5));
   }
-  const char* e1n[8] = {"start", "x_done1+dh1c", "A1 arrived", "x_done2+read", "z_done", "dz arrived", "w_done", "y arrived"};
+  const char* e1n[7] = {"start", "x_done1+dh1c", "w_done", "A1+X1 staged, arrived", "x_done2+read", "z_done", "phase, arrived"};
   printf("== layer-1 worker (warp 8 lane 0): cycles since previous stamp, steps 3..6\n");
   for (int st = 3; st < 7; ++st) {
     printf(" step %d:", st);
-    for (int e = 0; e < 8; ++e) printf(" %s=%lld", e1n[e], tm(1, st * 8 + e) - tm(1, st * 8 + e - 1));
-    printf(" | step total %lld\n", tm(1, st * 8 + 7) - tm(1, (st - 1) * 8 + 7));
+    for (int e = 0; e < 7; ++e) printf(" %s=%lld", e1n[e], tm(1, st * 7 + e) - tm(1, st * 7 + e - 1));
+    printf(" | step total %lld\n", tm(1, st * 7 + 6) - tm(1, (st - 1) * 7 + 6));
   }
-  const char* ev[6] = {"Z2", "Z1", "dX2", "dX1", "dW2done", "dW1done"};
-  printf("== issuer events (cycles since previous event), events 18..47\n  ");
-  for (int k = 18; k < 48; ++k) printf(" %s+%lld", ev[p[2 * 4096 + k] & 7], tm(2, k) - tm(2, k - 1));
-  printf("\n== interleaving: absolute stamps (cycles since L2 step-3 start) L2 / L1 / issuer\n");
-  const long long t0 = tm(0, 3 * 7);
+  const char* ev[4] = {"Z2", "Z1", "dX2+dW2", "dX1+dW1"};
+  printf("== issuer events, absolute (cycles since L2 step-3 start)\n  ");
+  for (int k = 4; k < 40; ++k) { const long long dt = tm(2, k) - tm(0, 3 * 6); if (dt > -12000 && dt < 40000) printf(" %s@%lld", ev[p[2 * 4096 + k] & 3], dt); }
+  printf("\n== interleaving: absolute stamps (cycles since L2 step-3 start)\n");
+  const long long t0 = tm(0, 3 * 6);
   for (int st = 3; st < 6; ++st) {
-    printf(" L2 step %d:", st); for (int e = 0; e < 7; ++e) printf(" %lld", tm(0, st * 7 + e) - t0); printf("\n");
-    printf(" L1 step %d:", st); for (int e = 0; e < 8; ++e) printf(" %lld", tm(1, st * 8 + e) - t0); printf("\n");
+    printf(" L2 step %d:", st); for (int e = 0; e < 6; ++e) printf(" %lld", tm(0, st * 6 + e) - t0); printf("\n");
+    printf(" L1 step %d:", st); for (int e = 0; e < 7; ++e) printf(" %lld", tm(1, st * 7 + e) - t0); printf("\n");
   }
   return 0;
 }
