@@ -251,7 +251,10 @@ def quick_measure(workload, steps, warmup, with_cpu=True):
             out["vs_cpu_baseline"] = out["value"] / out["cpu_baseline"]["value"]
         except Exception as ex:
             out["cpu_baseline"] = {"error": repr(ex)[:200]}
+    prog._graphs.clear()
     del sess, ms, prog, optimizer, problem
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     return out
 

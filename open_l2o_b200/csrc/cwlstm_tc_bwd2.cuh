@@ -106,49 +106,51 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// ---- 10-unit chunking: every chunk is naturally aligned for the 16/8-byte global accesses and the x4/x2 (one column
-// per unit) and x16/x8 (four gate columns per unit) TMEM accesses.  HALF 0: units 0..9 as 4|4|2, HALF 1: units
-// 10..19 as 2|4|4.
-template <int HALF, class F>
-__device__ __forceinline__ void chunks10(F&& f) {
-  if constexpr (HALF == 0) {
-    f(IC<0>{}, IC<4>{});
-    f(IC<4>{}, IC<4>{});
-    f(IC<8>{}, IC<2>{});
-  } else {
-    f(IC<0>{}, IC<2>{});
-    f(IC<2>{}, IC<4>{});
-    f(IC<6>{}, IC<4>{});
-  }
+// ---- 10-unit chunking -------------------------------------------------------------------------------------------
+// A thread owns 10 hidden units of one layer, walked as three chunks of 4 | 4 | 2 units.  Half 0 owns units 0..9 as
+// [0-3][4-7][8-9]; half 1 owns units 10..19 walked as [12-15][16-19][10-11], i.e. the SAME chunk shapes with different
+// base units, so both halves (and every lane quarter) execute ONE instruction stream: the half is a run-time value
+// (ncu r02e: 23 % of the stall samples of the per-half-specialised kernel were instruction-fetch stalls, the four
+// role-specialised epilogues being 4 x 27 KB of code).  Every chunk stays naturally aligned for the 16/8-byte global
+// accesses, the x4/x2 (one column per unit) and x16/x8 (four gate columns per unit) TMEM accesses and the 16-byte
+// staging groups.  f(K0, NC, ub): K0 = index of the chunk's first unit in the thread's arrays, NC = units in the
+// chunk (both compile-time), ub = the chunk's first hidden unit (run-time).
+struct UnitMap {
+  int u0, u1, u2;   // base units of the three chunks
+  __device__ __forceinline__ explicit UnitMap(int half) : u0(half ? 12 : 0), u1(half ? 16 : 4), u2(half ? 10 : 8) {}
+};
+template <class F>
+__device__ __forceinline__ void chunks10(const UnitMap& um, F&& f) {
+  f(IC<0>{}, IC<4>{}, um.u0);
+  f(IC<4>{}, IC<4>{}, um.u1);
+  f(IC<8>{}, IC<2>{}, um.u2);
 }
-template <int HALF>
-__device__ __forceinline__ void load10(const float* __restrict__ p, float* v) {  // p -> unit U0 of the row
-  chunks10<HALF>([&](auto k0c, auto ncc) {
+#define L2O_CHUNK3(K0, NC, k0c, ncc) L2O_CHUNK(K0, NC, k0c, ncc)
+__device__ __forceinline__ void load10(const UnitMap& um, const float* __restrict__ p, float* v) {  // p -> unit 0 of the row
+  chunks10(um, [&](auto k0c, auto ncc, int ub) {
     L2O_CHUNK(K0, NC, k0c, ncc);
     if constexpr (NC == 4) {
-      const float4 t = *reinterpret_cast<const float4*>(p + K0);
+      const float4 t = *reinterpret_cast<const float4*>(p + ub);
       v[K0] = t.x; v[K0 + 1] = t.y; v[K0 + 2] = t.z; v[K0 + 3] = t.w;
     } else {
-      const float2 t = *reinterpret_cast<const float2*>(p + K0);
+      const float2 t = *reinterpret_cast<const float2*>(p + ub);
       v[K0] = t.x; v[K0 + 1] = t.y;
     }
   });
 }
-// 10 per-unit values -> TMEM columns [col0, col0+10) as 3xTF32 hi (at t_hi) / lo (at t_lo)
-template <int HALF>
-__device__ __forceinline__ void st_split10(uint32_t t_hi, uint32_t t_lo, int col0, const float* v) {
-  chunks10<HALF>([&](auto k0c, auto ncc) {
+// 10 per-unit values -> TMEM columns col0 + unit as 3xTF32 hi (at t_hi) / lo (at t_lo)   (col0 = column of unit 0)
+__device__ __forceinline__ void st_split10(const UnitMap& um, uint32_t t_hi, uint32_t t_lo, int col0, const float* v) {
+  chunks10(um, [&](auto k0c, auto ncc, int ub) {
     L2O_CHUNK(K0, NC, k0c, ncc);
-    if constexpr (NC == 4) st_split4(t_hi, t_lo, col0 + K0, v + K0);
-    else st_split2(t_hi, t_lo, col0 + K0, v + K0);
+    if constexpr (NC == 4) st_split4(t_hi, t_lo, col0 + ub, v + K0);
+    else st_split2(t_hi, t_lo, col0 + ub, v + K0);
   });
 }
-// 10 per-unit columns [col0, col0+10) of this thread's lane -> registers (loads in flight behind one wait)
-template <int HALF>
-__device__ __forceinline__ void ld10(uint32_t t_base, int col0, float* v) {
-  chunks10<HALF>([&](auto k0c, auto ncc) {
+// per-unit columns col0 + unit of this thread's lane -> registers (loads in flight behind one wait)
+__device__ __forceinline__ void ld10(const UnitMap& um, uint32_t t_base, int col0, float* v) {
+  chunks10(um, [&](auto k0c, auto ncc, int ub) {
     L2O_CHUNK(K0, NC, k0c, ncc);
-    tmem_ldn<NC>(t_base + col0 + K0, v + K0);
+    tmem_ldn<NC>(t_base + col0 + ub, v + K0);
   });
   tc_wait_ld();
 }
@@ -195,26 +197,11 @@ __device__ __forceinline__ void stage16(uint32_t yh, uint32_t yl, int c, int s, 
     sts32(yl + off, l[0]);
   }
 }
-// the thread's 10 per-unit values -> slots [s0 + U0, s0 + U0 + 10)
-template <int HALF>
-__device__ __forceinline__ void stage_units10(uint32_t yh, uint32_t yl, int c, int s0, const float* v) {
-  constexpr int U0 = HALF * kNU;
-  chunks10<HALF>([&](auto k0c, auto ncc) {
+// the thread's 10 per-unit values -> slots s0 + unit   (s0 = slot of unit 0)
+__device__ __forceinline__ void stage_units10(const UnitMap& um, uint32_t yh, uint32_t yl, int c, int s0, const float* v) {
+  chunks10(um, [&](auto k0c, auto ncc, int ub) {
     L2O_CHUNK(K0, NC, k0c, ncc);
-    stage16<NC>(yh, yl, c, s0 + U0 + K0, v + K0);
-  });
-}
-// re-read this thread's dZ columns (hi part == the exact fp32 value, see split_tf32) and stage them as bf16 hi/lo
-template <int HALF>
-__device__ __forceinline__ void stage_dz(uint32_t t_z, uint32_t yh, uint32_t yl, int c) {
-  constexpr int U0 = HALF * kNU;
-  chunks10<HALF>([&](auto k0c, auto ncc) {
-    L2O_CHUNK(K0, NC, k0c, ncc);
-    float dz[4 * NC];
-    tmem_ldn<4 * NC>(t_z + 4 * (U0 + K0), dz);
-    tc_wait_ld();
-#pragma unroll
-    for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * (U0 + K0) + 8 * g8, dz + 8 * g8);
+    stage16<NC>(yh, yl, c, s0 + ub, v + K0);
   });
 }
 
@@ -294,10 +281,11 @@ __device__ __forceinline__ void flush_dw1(const l2o_bwd_args& a, uint32_t tl, in
 // =====================================================================================================================
 // layer-2 workers: output layer + layer-2 LSTM backward
 // =====================================================================================================================
-template <class C, int HALF>
+template <class C>
 __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt& rt, SmemB2& S, uint32_t tmem_base, int warp,
                                               int lane) {
-  constexpr int U0 = HALF * kNU;
+  const int half = (warp >> 2) & 1;   // run-time: both halves share one instruction stream
+  const UnitMap um(half);
   const int q = warp & 3;
   const int c = q * 32 + lane;
   const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -310,12 +298,12 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
   uint32_t pz = 0, px = 0, pw = 0;
   bool have_prev = false;
   int pi = 0;
-  const bool prof = (HALF == 0 && q == 0 && lane == 0);
+  const bool prof = (half == 0 && q == 0 && lane == 0);
   (void)pi; (void)prof;
   float acc_wo[kNU], acc_bo = 0.f;
 #pragma unroll
   for (int k = 0; k < kNU; ++k) acc_wo[k] = 0.f;
-  if (HALF == 0) {  // zero the persistent dW2^T accumulators (lane = slot row); layer-1 half 0 does dW1^T
+  if (half == 0) {  // zero the persistent dW2^T accumulators (lane = slot row); layer-1 half 0 does dW1^T
 #pragma unroll
     for (int k = 0; k < 48 / 4; ++k) tmem_st4(tl + cW2 + 4 * k, 0.f, 0.f, 0.f, 0.f);
     tc_wait_st();
@@ -338,13 +326,13 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
 #pragma unroll
         for (int k = 0; k < kNU; ++k) { h1n[k] = 0.f; h2p[k] = 0.f; c2p[k] = 0.f; }
         if (act) {
-          load10<HALF>(ck + slot + i * kH + U0, h1n);
-          load10<HALF>(ck + 2 * n * kH + i * kH + U0, h2p);
-          load10<HALF>(ck + 2 * n * kH + (n + i) * kH + U0, c2p);
+          load10(um, ck + slot + i * kH, h1n);
+          load10(um, ck + 2 * n * kH + i * kH, h2p);
+          load10(um, ck + 2 * n * kH + (n + i) * kH, c2p);
           if (t > 0) {  // pull the following step's rows towards L2
             const float* nk = ck - slot;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + U0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + U0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + i * kH + um.u2));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + 2 * n * kH + (n + i) * kH + um.u2));
           }
         }
         if (imit && act) lam = (a.delta_seq[(int64_t)t * n + i] - a.labels[(int64_t)t * n + i]) * inv_nt;
@@ -353,16 +341,16 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
           mbar_wait(&S.x_done[0], px);  // dZ2-lo / A2 region becomes writable
           px ^= 1;
           tc_fence_after();
-          if (t != T - 1) ld10<HALF>(tX, kA2H2P + U0, dh2c);
+          if (t != T - 1) ld10(um, tX, kA2H2P, dh2c);
         }
         if (prof) { L2O_PROF2(0, pi, 1); ++pi; }
         if (t == T - 1) {
 #pragma unroll
           for (int k = 0; k < kNU; ++k) dh2c[k] = 0.f;
         }
-        st_split10<HALF>(tRh, tRl, kA2H1N + U0, h1n);
-        st_split10<HALF>(tRh, tRl, kA2H2P + U0, h2p);
-        if (HALF == 1) {  // constant columns 0..7: zero-weight rows + the bias 1 at 4+F
+        st_split10(um, tRh, tRl, kA2H1N, h1n);
+        st_split10(um, tRh, tRl, kA2H2P, h2p);
+        if (half == 1) {  // constant columns 0..7: zero-weight rows + the bias 1 at 4+F
           float one[4] = {0.f, 0.f, 0.f, 0.f};
           one[C::F] = 1.0f;
           tmem_st4(tRh, 0.f, 0.f, 0.f, 0.f);
@@ -370,12 +358,16 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
           tmem_st4(tRh + kA2One, one[0], one[1], one[2], one[3]);
           tmem_st4(tRl + kA2One, 0.f, 0.f, 0.f, 0.f);
         }
-        // X2 row of the dW2^T operand, from the same registers.  The previous step's dW2 MMAs were issued right behind
-        // its dX2 MMAs and have drained long before this point (the wait is a formality except under contention).
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&S.a_ready[0]);
+        if (prof) { L2O_PROF2(0, pi, 2); ++pi; }
+        // X2 row of the dW2^T operand, from the same registers, in the shadow of the Z2 round trip.  The previous step's
+        // dW2 MMAs were issued right behind its dX2 MMAs; by now they have drained (the wait is a formality).
         if (have_prev) {
           mbar_wait(&S.w_done[0], pw);
           pw ^= 1;
-          if (t == T - 1 && HALF == 0) {   // first step of a new tile: drain the previous tile's dW2^T accumulators
+          if (t == T - 1 && half == 0) {   // first step of a new tile: drain the previous tile's dW2^T accumulators
             tc_fence_after();
             flush_dw2<C>(a, tl, c);
             tc_fence_before();
@@ -383,33 +375,29 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
           }
         }
         if (prof) { L2O_PROF2(0, pi, 5); ++pi; }
-        stage_units10<HALF>(yh, yl, c, 0, h1n);
-        stage_units10<HALF>(yh, yl, c, kX2H2P, h2p);
+        stage_units10(um, yh, yl, c, 0, h1n);
+        stage_units10(um, yh, yl, c, kX2H2P, h2p);
       }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(&S.a_ready[0]);
-      if (prof) { L2O_PROF2(0, pi, 2); ++pi; }
       // ---- layer-2 gates, output layer, layer-2 backward: dZ2 -> TMEM (hi in place, lo over A2) + bf16 staging ------
       const float dy = rt.scale * lam;
-      if (HALF == 1) acc_bo += dy;
+      if (half == 1) acc_bo += dy;
       mbar_wait(&S.z_done[0], pz);
       pz ^= 1;
       tc_fence_after();
       if (prof) { L2O_PROF2(0, pi, 3); ++pi; }
-      chunks10<HALF>([&](auto k0c, auto ncc) {
+      chunks10(um, [&](auto k0c, auto ncc, int ub) {
         L2O_CHUNK(K0, NC, k0c, ncc);
         float z[4 * NC], hn[NC], dh[NC];
-        tmem_ldn<4 * NC>(tZ + 4 * (U0 + K0), z);
+        tmem_ldn<4 * NC>(tZ + 4 * ub, z);
 #pragma unroll
-        for (int u = 0; u < NC; ++u) dh[u] = fmaf(S.wo[U0 + K0 + u], dy, dh2c[K0 + u]);
+        for (int u = 0; u < NC; ++u) dh[u] = fmaf(S.wo[ub + u], dy, dh2c[K0 + u]);
         tc_wait_ld();
         chunk_bwd<NC>(z, c2p + K0, dh, dc2 + K0, hn);
 #pragma unroll
         for (int u = 0; u < NC; ++u) acc_wo[K0 + u] = fmaf(hn[u], dy, acc_wo[K0 + u]);
-        put_dz<NC>(tZ, tDl, 4 * (U0 + K0), z);
+        put_dz<NC>(tZ, tDl, 4 * ub, z);
 #pragma unroll
-        for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * (U0 + K0) + 8 * g8, z + 8 * g8);
+        for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * ub + 8 * g8, z + 8 * g8);
       });
       fence_proxy_async();
       tc_wait_st();
@@ -426,9 +414,10 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
     float v = acc_wo[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) atomicAdd(&a.dtheta[C::O_WO + U0 + k], (double)v);
+    const int unit = (k < 4 ? um.u0 : (k < 8 ? um.u1 - 4 : um.u2 - 8)) + k;   // array index -> hidden unit
+    if (lane == 0) atomicAdd(&a.dtheta[C::O_WO + unit], (double)v);
   }
-  if (HALF == 1) {
+  if (half == 1) {
     float v = acc_bo;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -440,16 +429,17 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
     pw ^= 1;
   }
   tc_fence_after();
-  if (HALF == 0) flush_dw2<C>(a, tl, c);
+  if (half == 0) flush_dw2<C>(a, tl, c);
 }
 
 // =====================================================================================================================
 // layer-1 workers
 // =====================================================================================================================
-template <class C, int HALF>
+template <class C>
 __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt& rt, SmemB2& S, uint32_t tmem_base, int warp,
                                               int lane) {
-  constexpr int U0 = HALF * kNU;
+  const int half = (warp >> 2) & 1;   // run-time: both halves share one instruction stream
+  const UnitMap um(half);
   const int q = warp & 3;
   const int c = q * 32 + lane;
   const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -460,9 +450,9 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
   uint32_t pz = 0, px = 0, pw = 0, px2 = 0;
   bool have_prev = false;
   int pi = 0;
-  const bool prof = (HALF == 0 && q == 0 && lane == 0);
+  const bool prof = (half == 0 && q == 0 && lane == 0);
   (void)pi; (void)prof;
-  if (HALF == 0) {
+  if (half == 0) {
 #pragma unroll
     for (int k = 0; k < 32 / 4; ++k) tmem_st4(tl + cW1 + 4 * k, 0.f, 0.f, 0.f, 0.f);
     tc_wait_st();
@@ -485,16 +475,16 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
         for (int k = 0; k < kNU; ++k) { h1p[k] = 0.f; c1p[k] = 0.f; }
         float raw0 = 0.f;
         if (act) {
-          load10<HALF>(ck + i * kH + U0, h1p);
-          load10<HALF>(ck + (n + i) * kH + U0, c1p);
-          if (HALF == 1) raw0 = a.in_seq[(int64_t)t * n + i];
+          load10(um, ck + i * kH, h1p);
+          load10(um, ck + (n + i) * kH, c1p);
+          if (half == 1) raw0 = a.in_seq[(int64_t)t * n + i];
           if (t > 0) {
             const float* nk = ck - slot;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + U0));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + U0));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + um.u2));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + um.u2));
           }
         }
-        if (HALF == 1) {
+        if (half == 1) {
           float uu[C::F];
           preprocess<C>(nullptr, rt, raw0, 0.f, uu);
 #pragma unroll
@@ -505,20 +495,24 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
           mbar_wait(&S.x_done[1], px);
           px ^= 1;
           tc_fence_after();
-          if (t != T - 1) ld10<HALF>(tX, U0, dh1);
+          if (t != T - 1) ld10(um, tX, 0, dh1);
         }
         if (prof) { L2O_PROF2(1, pi, 1); ++pi; }
         if (t == T - 1) {
 #pragma unroll
           for (int k = 0; k < kNU; ++k) dh1[k] = 0.f;
         }
-        st_split10<HALF>(tRh, tRl, U0, h1p);
-        if (HALF == 1) st_split4(tRh, tRl, kA1Chunk, u4);
-        // X1 row of the dW1^T operand from the same registers (the previous step's dW1 MMAs drained long ago)
+        st_split10(um, tRh, tRl, 0, h1p);
+        if (half == 1) st_split4(tRh, tRl, kA1Chunk, u4);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&S.a_ready[1]);
+        if (prof) { L2O_PROF2(1, pi, 2); ++pi; }
+        // X1 row of the dW1^T operand from the same registers, in the shadow of the Z1 round trip
         if (have_prev) {
           mbar_wait(&S.w_done[1], pw);
           pw ^= 1;
-          if (t == T - 1 && HALF == 0) {   // first step of a new tile: drain the previous tile's dW1^T accumulators
+          if (t == T - 1 && half == 0) {   // first step of a new tile: drain the previous tile's dW1^T accumulators
             tc_fence_after();
             flush_dw1<C>(a, tl, c);
             tc_fence_before();
@@ -526,20 +520,16 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
           }
         }
         if (prof) { L2O_PROF2(1, pi, 6); ++pi; }
-        stage_units10<HALF>(yh, yl, c, 0, h1p);
-        if (HALF == 1) stage16<4>(yh, yl, c, kX1Chunk, u4);
+        stage_units10(um, yh, yl, c, 0, h1p);
+        if (half == 1) stage16<4>(yh, yl, c, kX1Chunk, u4);
       }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(&S.a_ready[1]);
-      if (prof) { L2O_PROF2(1, pi, 2); ++pi; }
       // ---- dh1 += dX2(t)[h1n]  (layer 2 has finished step t) -----------------------------------------------------------
       mbar_wait(&S.x_done[0], px2);
       px2 ^= 1;
       tc_fence_after();
       {
         float v[kNU];
-        ld10<HALF>(tX2, kA2H1N + U0, v);
+        ld10(um, tX2, kA2H1N, v);
 #pragma unroll
         for (int k = 0; k < kNU; ++k) dh1[k] += v[k];
       }
@@ -551,15 +541,15 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
       pz ^= 1;
       tc_fence_after();
       if (prof) { L2O_PROF2(1, pi, 4); ++pi; }
-      chunks10<HALF>([&](auto k0c, auto ncc) {
+      chunks10(um, [&](auto k0c, auto ncc, int ub) {
         L2O_CHUNK(K0, NC, k0c, ncc);
         float z[4 * NC];
-        tmem_ldn<4 * NC>(tZ + 4 * (U0 + K0), z);
+        tmem_ldn<4 * NC>(tZ + 4 * ub, z);
         tc_wait_ld();
         chunk_bwd<NC>(z, c1p + K0, dh1 + K0, dc1 + K0, nullptr);
-        put_dz<NC>(tZ, tDl, 4 * (U0 + K0), z);
+        put_dz<NC>(tZ, tDl, 4 * ub, z);
 #pragma unroll
-        for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * (U0 + K0) + 8 * g8, z + 8 * g8);
+        for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * ub + 8 * g8, z + 8 * g8);
       });
       fence_proxy_async();
       tc_wait_st();
@@ -574,7 +564,7 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
     pw ^= 1;
   }
   tc_fence_after();
-  if (HALF == 0) flush_dw1<C>(a, tl, c);
+  if (half == 0) flush_dw1<C>(a, tl, c);
 }
 
 template <class C>
@@ -626,14 +616,8 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
 
   if (warp < kIssuerWarp) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs2));
-    const int half = (warp >> 2) & 1;
-    if (warp < 8) {
-      if (half == 0) layer2_worker<C, 0>(a, rt, S, tmem_base, warp, lane);
-      else layer2_worker<C, 1>(a, rt, S, tmem_base, warp, lane);
-    } else {
-      if (half == 0) layer1_worker<C, 0>(a, rt, S, tmem_base, warp, lane);
-      else layer1_worker<C, 1>(a, rt, S, tmem_base, warp, lane);
-    }
+    if (warp < 8) layer2_worker<C>(a, rt, S, tmem_base, warp, lane);
+    else layer1_worker<C>(a, rt, S, tmem_base, warp, lane);
   } else if (warp > kIssuerWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kIssRegs2));
   } else {

@@ -419,6 +419,35 @@ struct l2o_hrnn {
   int64_t* d_sizes;  // per-tensor counts the per-tensor means divide by (global sizes when sharded)
 };
 
+// A handle may be destroyed (Python GC) while another program is capturing a CUDA graph, and cudaFree during a capture
+// invalidates it: destroy parks the device buffers and the next l2o_hrnn_create (never inside a capture) frees them.
+namespace {
+struct Graveyard {
+  std::mutex mu;
+  std::vector<void*> ptrs;
+};
+Graveyard& graveyard() {
+  static Graveyard* g = new Graveyard();
+  return *g;
+}
+void bury(void* p) {
+  if (!p) return;
+  Graveyard& g = graveyard();
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.ptrs.push_back(p);
+}
+void free_buried() {
+  Graveyard& g = graveyard();
+  std::vector<void*> take;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    take.swap(g.ptrs);
+  }
+  for (void* p : take) cudaFree(p);
+}
+}  // namespace
+
+
 extern "C" {
 
 int l2o_hrnn_create(l2o_hrnn_handle* out, const int64_t* tensor_sizes, int32_t n_tensors) {
@@ -466,34 +495,6 @@ int l2o_hrnn_create(l2o_hrnn_handle* out, const int64_t* tensor_sizes, int32_t n
   *out = h;
   return L2O_OK;
 }
-
-// A handle may be destroyed (Python GC) while another program is capturing a CUDA graph, and cudaFree during a capture
-// invalidates it: destroy parks the device buffers and the next l2o_hrnn_create (never inside a capture) frees them.
-namespace {
-struct Graveyard {
-  std::mutex mu;
-  std::vector<void*> ptrs;
-};
-Graveyard& graveyard() {
-  static Graveyard* g = new Graveyard();
-  return *g;
-}
-void bury(void* p) {
-  if (!p) return;
-  Graveyard& g = graveyard();
-  std::lock_guard<std::mutex> lk(g.mu);
-  g.ptrs.push_back(p);
-}
-void free_buried() {
-  Graveyard& g = graveyard();
-  std::vector<void*> take;
-  {
-    std::lock_guard<std::mutex> lk(g.mu);
-    take.swap(g.ptrs);
-  }
-  for (void* p : take) cudaFree(p);
-}
-}  // namespace
 
 void l2o_hrnn_destroy(l2o_hrnn_handle h) {
   if (!h) return;

@@ -400,6 +400,8 @@ class HierarchicalRNN(object):
                     and all(a is b for a, b in zip(old[1], var_list)))
             if not same:
                 try:
+                    import gc
+                    gc.collect()   # no finaliser (old CUDAGraph pools, handles) may run inside the capture
                     torch.cuda.synchronize()
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):

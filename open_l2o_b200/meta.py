@@ -425,6 +425,10 @@ class _Program(object):
             return self._graph_body(train, step0)
         if key not in self._graphs:
             try:
+                # garbage from earlier programs (their CUDAGraph objects free device memory when collected) must not be
+                # finalised in the middle of this capture: a cudaFree during capture invalidates it
+                import gc
+                gc.collect()
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 n0 = _engine.launch_count()

@@ -32,14 +32,14 @@ int main() {
   std::vector<long long> p(3 * 4096);
   cudaMemcpyFromSymbol(p.data(), tcb2::g_prof2, sizeof(long long) * 3 * 4096);
   auto tm = [&](int role, int idx) { return p[role * 4096 + idx] >> 3; };
-  const char* e2[6] = {"start", "x_done+dh2c", "w_done", "A2+X2 staged, arrived", "z_done", "phase (dz staged), arrived"};
+  const char* e2[6] = {"start", "x_done+dh2c", "A2 arrived", "w_done", "X2 staged + z_done", "phase (dz staged), arrived"};
   printf("== layer-2 worker (warp 0 lane 0): cycles since previous stamp, steps 3..6\n");
   for (int st = 3; st < 7; ++st) {
     printf(" step %d:", st);
     for (int e = 0; e < 6; ++e) printf(" %s=%lld", e2[e], tm(0, st * 6 + e) - tm(0, st * 6 + e - 1));
     printf(" | step total %lld\n", tm(0, st * 6 + 5) - tm(0, (st - 1) * 6 + 5));
   }
-  const char* e1n[7] = {"start", "x_done1+dh1c", "w_done", "A1+X1 staged, arrived", "x_done2+read", "z_done", "phase, arrived"};
+  const char* e1n[7] = {"start", "x_done1+dh1c", "A1 arrived", "w_done", "X1 staged + x_done2+read", "z_done", "phase, arrived"};
   printf("== layer-1 worker (warp 8 lane 0): cycles since previous stamp, steps 3..6\n");
   for (int st = 3; st < 7; ++st) {
     printf(" step %d:", st);
