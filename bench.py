@@ -612,7 +612,7 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak = float(peaks.get("bf16_tflops", 1700.0))   # burst figure: the kernels are timed alone (launch, sync)
         fl = FLOP_PER_UPDATE_INFER[netkind]
         ach_b = 2.0 * fl * r.n * T / t_b / 1e12          # backward = two more GEMMs of the forward's shape
         ach_f = fl * r.n * T / t_f / 1e12
@@ -624,10 +624,10 @@ def main():
         except Exception:
             pass
         alg_bytes = (C_SF_BYTES + 8) * r.n * T      # checkpoint row + g_rec + in_seq per coordinate-update (read)
-        roof = {"bound": "tensor", "kernel": "tcb::unroll_bwd_kernel (tcgen05 BPTT)", "achieved": ach_b, "peak": peak,
+        roof = {"bound": "tensor", "kernel": "tcb2::unroll_bwd2_kernel (layer-pipelined tcgen05 BPTT)", "achieved": ach_b, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach_b / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": alg_bytes,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF",
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if peaks else "fallback 1.7 PF (B200_PROFILING.md)",
                 "fwd_kernel": {"name": "tc::unroll_fwd_kernel (tcgen05)", "achieved": ach_f, "frac": ach_f / peak,
                                "ms": 1e3 * t_f, "coord_updates_per_s": r.n * T / t_f},
                 "bwd_ms": 1e3 * t_b, "bwd_coord_updates_per_s": r.n * T / t_b,
@@ -639,9 +639,13 @@ def main():
                                 "checkpoint row: 320 B + g 4 B + net input 4 B = 328 B per coordinate-update per "
                                 "direction = `algorithmic_bytes`; the measured DRAM traffic is ~41x the 8 B figure and "
                                 "1.01x the checkpoint figure",
-                "notes": "fp32 parity => 3xTF32 (tf32 = 1/2 bf16 rate): a 100%-busy tensor pipe reads 1/6 of this peak "
-                         "(ncu: tensor pipe 30% active in this kernel, 22% in the forward kernel); the activation pipe "
-                         "(320 MUFU ops per coordinate-update forward, 400 backward) caps the path near 1.4e10 upd/s/GPU"}
+                "notes": "fp32 parity => 3xTF32 for the gate recompute and dX (tf32 = 1/2 the bf16 rate: a 100%-busy tensor "
+                         "pipe reads 1/6 of this peak) and bf16 hi/lo for dW^T; ncu r02e: tensor pipe 28%, issue slots "
+                         "36%, XU 28%, warps active 31% in the BPTT kernel (profiles/r02_ncu_summary.json); the kernel is "
+                         "bound by instruction issue inside the two overlapping layer phases (130 warp-instructions per "
+                         "coordinate-update, 30% of them operand splitting) and by the serial MMA round trips of each chain; "
+                         "the activation pipe (320 MUFU ops per coordinate-update forward, 400 backward) caps the path "
+                         "near 1.4e10 upd/s/GPU"}
 
     if roof is None:      # external-gradient workloads: HBM roofline of the step kernel (+ BPTT) on this workload
         roof = external_roofline(prog, netkind, T, t_dev / args.steps)
