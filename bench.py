@@ -240,8 +240,10 @@ def quick_measure(workload, steps, warmup, with_cpu=True):
     t = e0.elapsed_time(e1) / 1e3
     launches = int(eng.launch_count() - l0)
     out = {"workload": desc, "coords": prog.N, "unroll": T, "mode": "train (fwd+BPTT+Adam)",
-           "regime": "fused" if prog.fused is not None else "external-gradient (torch autograd between step kernels, "
-           "one captured CUDA graph per unroll)", "value": prog.N * T * steps / t, "unit": "coordinate-updates/s",
+           "regime": "fused" if prog.fused is not None else (
+               "external-gradient (%s between step kernels, one captured CUDA graph per unroll)" % (
+                   "gradient producer '%s'" % prog.producer.kind if prog.producer is not None else "torch autograd")),
+           "value": prog.N * T * steps / t, "unit": "coordinate-updates/s",
            "ms_per_step": 1e3 * t / steps, "steps": steps, "warmup": warmup,
            "gpu_launches": launches, "last_fx": cost, "net_scale": NET_SCALE[workload]}
     out["roofline"] = external_roofline(prog, netkind, T, t / steps)
@@ -723,7 +725,9 @@ def main():
             "config": {"workload": desc if not strong else desc.replace("d=1e6 per GPU", "d=%d in total" % total_coords),
                        "coords_per_gpu": coords, "coords_total": job_coords, "unroll": T,
                        "mode": "train (fwd+BPTT+Adam)",
-                       "regime": "fused" if prog.fused is not None else "external-gradient",
+                       "regime": "fused" if prog.fused is not None else (
+                           "external-gradient (producer %s)" % prog.producer.kind if prog.producer is not None
+                           else "external-gradient (torch autograd)"),
                        "engine": args.engine, "parallelism": "dp%d (coordinates sharded)" % world,
                        "net_scale": NET_SCALE[args.workload], "theta_check": theta_check,
                        "l2_policy": "working set (checkpoints %.1f GB/GPU) >> 126 MB L2" % (r.ckpt.numel() * 4 / 1e9),

@@ -651,9 +651,7 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
     uint32_t pA[2] = {0, 0}, pD[2] = {0, 0}, pF[2] = {0, 0}, pT = 0;
     int pi = 0;
     (void)pi;
-    int dw_left[2] = {0, 0};                          // K-steps of the layer's current dW batch still to issue
-    bool dw_over[2] = {false, false};                 // ... whose first MMA overwrites (first step of a tile)
-    while (nD[0] < total || nD[1] < total || dw_left[0] > 0 || dw_left[1] > 0) {
+    while (nD[0] < total || nD[1] < total) {
 #pragma unroll
       for (int l = 0; l < 2; ++l) {
         // A(t): gate recompute Z_l = A_l . B_l'
@@ -715,33 +713,19 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
               }
             }
             tc_commit(&S.x_done[l]);
-          }
-          __syncwarp();
-          L2O_PROF2(2, pi, l == 0 ? 2 : 3); ++pi;
-          dw_left[l] = 8;
-          dw_over[l] = first_of_tile;
-        }
-      }
-      // dW_l^T batches (24 SS-mode MMAs, ~1.1 K cycles on the in-order tensor pipe) start right behind their dX but go
-      // in two K-steps per poll, so the OTHER layer's Z / dX request never waits for more than ~270 cycles of them
-#pragma unroll
-      for (int l = 0; l < 2; ++l) {
-        if (dw_left[l] > 0) {
-          if (elect_one()) {
             const uint64_t yh0 = l == 0 ? y2h : y1h, yl0 = l == 0 ? y2l : y1l;
             const uint32_t d = tb + (l == 0 ? cW2 : cW1);
             const uint32_t id = l == 0 ? id_dw2 : id_dw1;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int kb = 8 - dw_left[l] + q;
-              mma_bf16_ss(d, yl0 + kb * kY16Step, yh0 + kb * kY16Step, id, (kb == 0 && dw_over[l]) ? 0u : 1u);
+            for (int kb = 0; kb < 8; ++kb) {
+              mma_bf16_ss(d, yl0 + kb * kY16Step, yh0 + kb * kY16Step, id, (kb == 0 && first_of_tile) ? 0u : 1u);
               mma_bf16_ss(d, yh0 + kb * kY16Step, yl0 + kb * kY16Step, id, 1u);
               mma_bf16_ss(d, yh0 + kb * kY16Step, yh0 + kb * kY16Step, id, 1u);
             }
-            if (dw_left[l] == 2) tc_commit(&S.w_done[l]);
+            tc_commit(&S.w_done[l]);
           }
           __syncwarp();
-          dw_left[l] -= 2;
+          L2O_PROF2(2, pi, l == 0 ? 2 : 3); ++pi;
         }
       }
     }

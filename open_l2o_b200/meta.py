@@ -26,7 +26,7 @@ from . import engine as _engine
 from . import networks
 from .variables import variable_getter
 
-_PRODUCER_KINDS = ("lasso_batch",)
+_PRODUCER_KINDS = ("lasso_batch", "mlp_xent")
 MetaLoss = collections.namedtuple("MetaLoss", "loss, update, reset, fx, x")
 MetaStep = collections.namedtuple("MetaStep", "step, update, reset, fx, x")
 
@@ -180,7 +180,8 @@ class _Program(object):
         self.X = torch.zeros(self.N, device=self.device)
         self.const_vals = {}
         self.fused = getattr(make_loss, "fused", None) if os.environ.get("L2O_DISABLE_FUSED") != "1" else None
-        if self.fused is not None and not (len(self.runs) == 1 and len(self.variables) == 1 and self.runs[0].n == self.N):
+        one_net = len(self.runs) == 1 and self.runs[0].n == self.N
+        if self.fused is not None and not (one_net and (len(self.variables) == 1 or self.fused.kind == "mlp_xent")):
             self.fused = None
         # "producer" optimizees: f and df/dx come from ONE library kernel per step instead of
         # torch autograd (~15 launches); the unroll stays step-at-a-time (the gradient couples coordinates) and is
@@ -305,6 +306,14 @@ class _Program(object):
         if p.kind == "lasso_batch":
             _engine.lasso_grad(self.const_vals[p.a], self.const_vals[p.b], Xflat, p.alpha, g, f=fx,
                                scale=self.scale_flat if self.scale_active else None)
+        elif p.kind == "mlp_xent":
+            from .problems import mlp_value_and_grad
+            with torch.no_grad():
+                xs = Xflat * self.scale_flat if self.scale_active else Xflat    # f(x (.) scale), DM/meta_dm_train.py:384
+                fx = mlp_value_and_grad(self._var_views(xs), self.const_vals[p.a], self.const_vals[p.b],
+                                        p.extra["activation"], self._var_views(g)).double()
+                if self.scale_active:
+                    g.mul_(self.scale_flat)
         else:
             raise ValueError(p.kind)
         return fx, g

@@ -24,6 +24,7 @@ class FusedSpec:
     alpha: float = 10.0
     fscale: float = 1.0
     group: int = 0   # "quadratic_batch": coordinates per dense group
+    extra: dict = None   # producer-specific structure ("mlp_xent": activation, number of layers)
 
 
 def simple():
@@ -175,4 +176,34 @@ def mlp(layers=(100,), in_dim=784, n_classes=10, batch_size=128, activation="sig
                 h = act(h)
             k = width
         return torch.nn.functional.cross_entropy(h, labels.long())
+    # analytic producer: f and df/dx without the autograd engine (mlp_value_and_grad below)
+    build.fused = FusedSpec("mlp_xent", "mlp", "data", "labels", extra=dict(activation=activation,
+                                                                           n_layers=len(tuple(layers)) + 1))
     return build
+
+
+def mlp_value_and_grad(params, data, labels, activation, grads_out):
+    """Loss and gradient of the `mlp` optimizee written out by hand (the optimizee step feeding the hot path, SURVEY.md
+    8(f) row 4): the forward pass keeps the activations, the backward pass writes every dW = h^T dz / db = sum(dz)
+    STRAIGHT INTO the caller's gradient views - about a dozen launches (3 GEMMs per layer, fused elementwise) instead of
+    the ~30 of the autograd engine with its per-variable copies.  params / grads_out: [w0, b0, w1, b1, ...]."""
+    n_layers = len(params) // 2
+    hs, h = [data], data
+    for i in range(n_layers):
+        z = torch.addmm(params[2 * i + 1], h, params[2 * i])
+        if i < n_layers - 1:
+            h = torch.sigmoid(z) if activation == "sigmoid" else torch.relu(z)
+            hs.append(h)
+    lab = labels.long()
+    logp = torch.log_softmax(z, dim=1)
+    loss = -logp.gather(1, lab.unsqueeze(1)).mean()
+    dz = torch.exp(logp)
+    dz.scatter_add_(1, lab.unsqueeze(1), torch.full((lab.numel(), 1), -1.0, device=dz.device, dtype=dz.dtype))
+    dz.mul_(1.0 / lab.numel())
+    for i in reversed(range(n_layers)):
+        torch.mm(hs[i].t(), dz, out=grads_out[2 * i])
+        torch.sum(dz, dim=0, out=grads_out[2 * i + 1])
+        if i > 0:
+            dh = dz @ params[2 * i].t()
+            dz = dh * hs[i] * (1.0 - hs[i]) if activation == "sigmoid" else dh * (hs[i] > 0).to(dh.dtype)
+    return loss
