@@ -14,11 +14,14 @@
 //   0..9 parameter (BiasGRU hidden), 10 scl_decay, 11 inp_decay, 12 log_learning_rate, 13..16 grad_accum1..4,
 //   17..20 ms1..4  (HR:303-343; "true_param" duplicates x when use_attention=False and is not stored).
 #include <cstdint>
+#include <cstdlib>
 #include <new>
 #include <mutex>
 #include <vector>
 
 #include "l2o_internal.h"
+#include "cwlstm_ffma.cuh"   // helpers cwlstm_tc.cuh expects
+#include "cwlstm_tc.cuh"     // tcgen05 / TMEM / mbarrier wrappers, tf32 split
 
 namespace l2o {
 namespace hrnn {
@@ -37,7 +40,8 @@ constexpr int O_G2D = 5883, O_LRM = 5887, O_OFF = 5888;
 constexpr int O_WG2 = 5889, O_BG2 = 7489, O_WC2 = 7529, O_BC2 = 8329;
 constexpr int kTheta = 8349;
 constexpr int kAcc = 24;  // per-tensor fp64 sums: [h'(10) | feat(12)], delta^2, log-lr'
-constexpr int kBlock = 256;
+constexpr int kBlock = 128;     // coordinates per block-table entry (= one tcgen05 tile)
+constexpr int kB0Stride = 32;   // floats per tensor in Workspace::bias0: r 0..9 | u 10..19 | c 20..29 | pad (16-byte rows)
 
 struct BlockEnt {
   int64_t start;  // first coordinate of the block (global index)
@@ -50,7 +54,7 @@ struct Workspace {
   double* acc;        // [nt][kAcc]
   int* any_nz;        // [nt][NS]   any(ms_i' != 0) seen this step
   int* zero_flag;     // [nt][NS]   all(ms_i == 0) for the step about to run (utils.py:128-130)
-  float* bias0;       // [nt][3*H0] per-tensor gate bias of the per-parameter GRU (HR:561-575)
+  float* bias0;       // [nt][kB0Stride] per-tensor gate bias of the per-parameter GRU (HR:561-575)
   float* inv_denom;   // [nt]
   float* mean_log_lr; // [1]
   float* upd;         // [N]
@@ -63,7 +67,7 @@ inline size_t carve(Workspace& w, void* base, int nt, int64_t n) {
   w.acc = (double*)take(sizeof(double) * nt * kAcc);
   w.any_nz = (int*)take(sizeof(int) * nt * NS);
   w.zero_flag = (int*)take(sizeof(int) * nt * NS);
-  w.bias0 = (float*)take(sizeof(float) * nt * 3 * H0);
+  w.bias0 = (float*)take(sizeof(float) * nt * kB0Stride);
   w.inv_denom = (float*)take(sizeof(float) * nt);
   w.mean_log_lr = (float*)take(sizeof(float));
   w.upd = (float*)take(sizeof(float) * (size_t)n);
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
   // (the 4x10 readout weights are read straight from theta through the read-only cache)
   if (tid < 2 * H0) sBg[tid] = theta[O_BG0 + tid];
   if (tid < H0) sBc[tid] = theta[O_BC0 + tid];
-  if (tid < 3 * H0) sB0[tid] = w.bias0[be.tensor * 3 * H0 + tid];
+  if (tid < 3 * H0) sB0[tid] = w.bias0[be.tensor * kB0Stride + tid];
   __syncthreads();
 
   const bool act = tid < be.count;
@@ -256,6 +260,8 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
   }
 }
 
+#include "hrnn_tc.cuh"
+
 // state scan used by l2o_hrnn_prepare: per-tensor sum of log-lr and any(ms_i != 0)
 __global__ void __launch_bounds__(kBlock) scan_kernel(const float* __restrict__ state, int64_t n,
                                                       const BlockEnt* __restrict__ blocks, Workspace w) {
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(64) tensor_kernel(const float* __restrict__ th
       float a = 0.f, b = 0.f;
       for (int k = 0; k < H1; ++k) a = fmaf(layer[j * H1 + k], theta[O_PM + k * 3 * H0 + o], a);
       for (int k = 0; k < H2; ++k) b = fmaf(sG[k], theta[O_GM + k * 3 * H0 + o], b);
-      w.bias0[j * 3 * H0 + o] = (a + theta[O_PB + o]) + (b + theta[O_GB + o]);
+      w.bias0[j * kB0Stride + o] = (a + theta[O_PB + o]) + (b + theta[O_GB + o]);
     }
   }
   if (tid == 0) *w.mean_log_lr = (float)(sSum / (double)n_total);
@@ -447,6 +453,25 @@ void free_buried() {
 }
 }  // namespace
 
+
+// L2O_HRNN_FFMA=1 selects the exact-fp32 FFMA kernel for the per-parameter level (debugging / A-B runs); the default
+// is the tcgen05 kernel.
+static bool use_ffma_coord() {
+  static const bool v = [] {
+    const char* e = getenv("L2O_HRNN_FFMA");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+static int coord_tc_grid() {
+  static const int v = [] {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(tcg::coord_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return sms * tcg::kCtasPerSm;
+  }();
+  return v;
+}
 
 extern "C" {
 
@@ -569,7 +594,12 @@ int l2o_hrnn_step_local(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   Workspace w;
   carve(w, a->workspace, h->nt, h->n);
-  coord_kernel<<<h->nblocks, kBlock, 0, st>>>(a->theta, a->g, a->state, h->n, h->d_blocks, w);
+  if (use_ffma_coord()) {
+    coord_kernel<<<h->nblocks, kBlock, 0, st>>>(a->theta, a->g, a->state, h->n, h->d_blocks, w);
+  } else {
+    const int grid = h->nblocks < coord_tc_grid() ? h->nblocks : coord_tc_grid();
+    tcg::coord_tc_kernel<<<grid, tcg::kTile, 0, st>>>(a->theta, a->g, a->state, h->n, h->d_blocks, h->nblocks, w);
+  }
   L2O_CUDA_TRY(cudaGetLastError());
   l2o::count_launch();
   return L2O_OK;
