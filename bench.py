@@ -334,8 +334,8 @@ def quick_measure_hrnn(steps, warmup, T=20, batch=128):
         pass
     peak = float(peaks.get("hbm_gbs", 6500.0))
     ach = bytes_per * nbig / t_big / 1e9
-    out["roofline"] = {"bound": "hbm", "kernel": "l2o::hrnn::coord_kernel + apply_kernel (one l2o_hrnn_step)",
-                       "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    out["roofline"] = {"bound": "hbm", "kernel": "l2o::hrnn::tcg::coord_tc_kernel + tensor_kernel + apply_kernel (one l2o_hrnn_step)",
+                       "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": 174.41 * nbig,   # dram bytes of coord_tc_kernel per launch (ncu --set full, profiles/r02j_hrnn_coord_tc.raw.csv)
                        "coords": nbig, "ms": 1e3 * t_big, "coord_updates_per_s": nbig / t_big,
                        "algorithmic_bytes_per_coord_update": bytes_per,
                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.5 TB/s"}

@@ -384,13 +384,15 @@ __global__ void __launch_bounds__(64) tensor_kernel(const float* __restrict__ th
 }
 
 __global__ void __launch_bounds__(kBlock) apply_kernel(float* __restrict__ x, float* __restrict__ update_out,
-                                                       const BlockEnt* __restrict__ blocks, Workspace w) {
-  const BlockEnt be = blocks[blockIdx.x];
-  if ((int)threadIdx.x >= be.count) return;
-  const int64_t i = be.start + threadIdx.x;
-  const float u = w.upd[i] * w.inv_denom[be.tensor];
-  x[i] -= u;
-  if (update_out) update_out[i] = u;
+                                                       const BlockEnt* __restrict__ blocks, int nblocks, Workspace w) {
+  for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {   // a few entries per CTA: independent 128-byte rows in flight
+    const BlockEnt be = blocks[b];
+    if ((int)threadIdx.x >= be.count) continue;
+    const int64_t i = be.start + threadIdx.x;
+    const float u = w.upd[i] * w.inv_denom[be.tensor];
+    x[i] -= u;
+    if (update_out) update_out[i] = u;
+  }
 }
 
 __global__ void init_state_kernel(const float* __restrict__ theta, float* __restrict__ state, int64_t n,
@@ -613,7 +615,7 @@ int l2o_hrnn_step_finish(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream
   carve(w, a->workspace, h->nt, h->n);
   tensor_kernel<<<1, 64, 0, st>>>(a->theta, a->layer, a->global, h->nt, h->d_sizes, h->n_global, w, 0);
   L2O_CUDA_TRY(cudaGetLastError());
-  apply_kernel<<<h->nblocks, kBlock, 0, st>>>(a->x, a->update, h->d_blocks, w);
+  apply_kernel<<<(h->nblocks + 3) / 4, kBlock, 0, st>>>(a->x, a->update, h->d_blocks, h->nblocks, w);
   L2O_CUDA_TRY(cudaGetLastError());
   l2o::count_launch(2);
   return L2O_OK;
