@@ -20,7 +20,8 @@ run() {  # n scaling extra...
   fi
 }
 for sc in weak strong; do
-  for n in 1 $N; do
+  for n in 1 2 4 8; do
+    [ $n -gt $N ] && continue
     run $n $sc > $out/${tag}_${sc}_n$n.json 2> $out/${tag}_${sc}_n$n.err
     python - $out/${tag}_${sc}_n$n.json $sc $n <<'PY'
 import json,sys
