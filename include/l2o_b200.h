@@ -137,6 +137,8 @@ typedef struct {
   double* dtheta;       /* [P] += dL/dtheta */
   const float* delta_seq; /* optional [T][n], imitation mode: the deltas l2o_unroll_fwd recorded for this unroll; lets the
                              tensor-core BPTT form dDelta_t without recomputing the output layer (exact-fp32 engine ignores it) */
+  float* scratch;       /* optional [T][n][20] floats, fc(20) nets (RNNProp) only: hand-over buffer between the layer-2 and the
+                             layer-1 pass of the tensor-core BPTT; NULL keeps such a net on the exact-fp32 engine */
 } l2o_bwd_args;
 
 int l2o_net_create(l2o_handle* out, const l2o_net_desc* desc);

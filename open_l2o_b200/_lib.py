@@ -61,7 +61,7 @@ class UnrollArgs(C.Structure):
 
 class BwdArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("T", C.c_int32), ("theta", _fp), ("in_seq", _fp), ("ckpt", _fp), ("g_rec", _fp),
-                ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp), ("delta_seq", _fp)]
+                ("labels", _fp), ("n_total", C.c_int64), ("dtheta", _fp), ("delta_seq", _fp), ("scratch", _fp)]
 
 
 class LassoArgs(C.Structure):

@@ -353,6 +353,24 @@ __device__ __forceinline__ float ext_weight_bwd(const float* __restrict__ theta,
   return 0.f;
 }
 
+// fc(20) nets run the BPTT as two single-chain passes (cwlstm_tc_bwd2.cuh), each with its matrix in the layer-2 slots
+// (B2' | T2) of its own image.  pass 0: layer 2, A = [0..3 zero | 4 one | 5..7 zero | 8..27 h1n | 28..47 h2p];
+// pass 1: layer 1, A = [h1p 0..19 | fc outputs 20..39 | 40 one | 41..47 zero].
+template <class C>
+__device__ __forceinline__ float ext_weight_bwd_fc(const float* __restrict__ theta, int pass, int k, int n) {
+  const int u = n >> 2, g = n & 3;
+  const int col = g * kH + u;
+  if (pass == 0) {
+    if (k == 4) return theta[C::O_B2 + col];
+    if (k >= 8 && k < 8 + 2 * kH) return theta[C::O_W2 + (k - 8) * C::G2 + col];
+    return 0.f;
+  }
+  if (k < kH) return theta[C::O_W1 + (C::F + k) * C::G1 + col];
+  if (k < 2 * kH) return theta[C::O_W1 + (k - kH) * C::G1 + col];
+  if (k == 2 * kH) return theta[C::O_B1 + col];
+  return 0.f;
+}
+
 // mode 0: forward image (B1 | B2, hi/lo);  mode 1: BPTT image (B1' | B2' in the BPTT operand order, then T1 | T2)
 constexpr float kLog2e = 1.4426950408889634f;
 template <class C>
@@ -411,6 +429,26 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
         const int idx = timg_index(l2 ? kT2Rows : kT1Rows, k, n);
         (l2 ? t2h : t1h)[idx] = hi;
         (l2 ? t2l : t1l)[idx] = to_tf32(lo);
+      }
+    }
+  } else {   // fc nets: one image per pass, only the layer-2 slots are read
+    const int per = kK2 * kN + kT2Rows * kN;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * per; e += gridDim.x * blockDim.x) {
+      const int pass = e / per, r = e % per;
+      const bool tr = r >= kK2 * kN;
+      const int ee = tr ? r - kK2 * kN : r;
+      const int k = ee / kN, n = ee % kN;   // k = operand row (A column), n = interleaved gate column
+      const float w = ext_weight_bwd_fc<C>(theta, pass, k, n);
+      const float hi = to_tf32(w), lo = to_tf32(w - hi);
+      float* base = img + (size_t)pass * kImgAllFloats;
+      if (!tr) {
+        const int idx = img_index(k, n);
+        base[2 * kB1Floats + idx] = hi;
+        base[2 * kB1Floats + kB2Floats + idx] = lo;
+      } else {
+        const int idx = timg_index(kT2Rows, k, n);
+        base[kImgFloats + 2 * kT1Floats + idx] = hi;
+        base[kImgFloats + 2 * kT1Floats + kT2Floats + idx] = lo;
       }
     }
   }
@@ -533,9 +571,28 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
   const bool adam_mode = C::NIN == 2 && a.m != nullptr;   // fused RNNProp features (DM/meta_rnnprop_train.py:383-388)
   uint32_t pfull[2] = {0, 0};
   int kpair = 0;
+  // Step-at-a-time regime (STAGE): the parameter and the first input of the NEXT pair are loaded one pair ahead, so
+  // their DRAM latency hides behind this pair's two MMA round trips (the state rows already arrive through the TMA ring).
+  constexpr bool kAheadIn = STAGE;   // in_seq[i] is the first input of step 0 in every input layout
+  float x_ahead = 0.f, in_ahead = 0.f;
+  if (STAGE && HALF == 1) {
+    const int64_t i0 = (int64_t)blockIdx.x * kTileCoords + tile * 128 + row;
+    if (i0 < n) {
+      if (a.x) x_ahead = a.x[i0];
+      if (kAheadIn && !in_kernel_opt) in_ahead = a.in_seq[i0];
+    }
+  }
   for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++kpair) {
     const int64_t i = pair * kTileCoords + tile * 128 + row;
     const bool act = i < n;
+    const float x_cur = x_ahead, in_cur = in_ahead;
+    if (STAGE && HALF == 1) {
+      const int64_t inx = i + (int64_t)gridDim.x * kTileCoords;
+      if (inx < n) {
+        if (a.x) x_ahead = a.x[inx];
+        if (kAheadIn && !in_kernel_opt) in_ahead = a.in_seq[inx];
+      }
+    }
     if constexpr (!STAGE) {  // pull the NEXT pair's state rows towards L2: with T = 1 the loads below are the critical path
       const int64_t inx = i + (int64_t)gridDim.x * kTileCoords;
       if (inx < n) {
@@ -583,7 +640,7 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
           store_units<HALF>(a.ckpt + 2 * n * kH + i * kH + U0, h2);
           store_units<HALF>(a.ckpt + 2 * n * kH + (n + i) * kH + U0, c2);
         }
-        if (a.x) x = a.x[i];
+        if (HALF == 1) x = STAGE ? x_cur : (a.x ? a.x[i] : 0.f);   // only half 1 carries the parameter
         if (in_kernel_opt) { oa = a.opt_a[i]; ob = a.opt_b[i]; }
       }
       st_split_units<HALF>(t_ah, t_al, kColH1 + U0, h1);
@@ -599,10 +656,10 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
             optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, raw0);
             if (a.g_rec) a.g_rec[(int64_t)t * n + i] = raw0;
           } else if (C::NIN == 2 && !adam_mode) {   // operator surface: (m~, g~) given
-            raw0 = a.in_seq[((int64_t)t * 2) * n + i];
+            raw0 = (kAheadIn && t == 0) ? in_cur : a.in_seq[((int64_t)t * 2) * n + i];
             raw1 = a.in_seq[((int64_t)t * 2 + 1) * n + i];
           } else {
-            raw0 = a.in_seq[(int64_t)t * n + i];
+            raw0 = (kAheadIn && t == 0) ? in_cur : a.in_seq[(int64_t)t * n + i];
           }
         }
         if constexpr (C::FC) {

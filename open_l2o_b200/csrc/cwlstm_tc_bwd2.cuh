@@ -35,6 +35,7 @@ using namespace tc;
 constexpr int kEpiThreads2 = 512;              // 16 epilogue warps: 0-7 layer 2, 8-15 layer 1
 constexpr int kThreads2 = kEpiThreads2 + 128;  // + the warpgroup holding the issuer warp
 constexpr int kEpiRegs2 = 112, kIssRegs2 = 32; // setmaxnreg targets (pool: 640 x 96)
+constexpr int kSoloRegs2 = 152;                // workers of a single-chain pass (the idle chain's warps drop to 24)
 constexpr int kNU = 10;                        // hidden units per thread
 // TMEM columns
 constexpr int cZ2 = 0, cR2 = 80, cX2 = 176, cZ1 = 224, cR1 = 304, cX1 = 384, cW2 = 416, cW1 = 464;
@@ -68,6 +69,7 @@ struct SmemB2 {
   uint16_t y1l[kY16Elems];
   float img[kImgAllFloats];    // B1'h|B1'l|B2'h|B2'l (K-major) | T1h|T1l|T2h|T2l (transposed, K-major)
   float wo[kH + 4];
+  float win[64];               // fc nets: Win [2][20] | bin [20]
   uint64_t wbar;
   uint64_t a_ready[2], dz_ready[2];               // index 0 = layer 2, 1 = layer 1 (epilogue -> issuer, 256 arrivals)
   uint64_t z_done[2], x_done[2], w_done[2];       // issuer (tcgen05.commit) -> epilogue
@@ -138,6 +140,20 @@ __device__ __forceinline__ void load10(const UnitMap& um, const float* __restric
     }
   });
 }
+__device__ __forceinline__ void store10(const UnitMap& um, float* __restrict__ p, const float* v) {  // p -> unit 0 of the row
+  chunks10(um, [&](auto k0c, auto ncc, int ub) {
+    L2O_CHUNK(K0, NC, k0c, ncc);
+    if constexpr (NC == 4) *reinterpret_cast<float4*>(p + ub) = make_float4(v[K0], v[K0 + 1], v[K0 + 2], v[K0 + 3]);
+    else *reinterpret_cast<float2*>(p + ub) = make_float2(v[K0], v[K0 + 1]);
+  });
+}
+__device__ __forceinline__ int unit_of(const UnitMap& um, int k) {   // array index -> hidden unit
+  return (k < 4 ? um.u0 : (k < 8 ? um.u1 - 4 : um.u2 - 8)) + k;
+}
+// column of the constant 1 inside the 4-wide feature chunk of A2: behind the F <= 3 features, or first for fc nets
+// (their layer-1 inputs are the 20 fc outputs, not a chunk)
+template <class C>
+struct Bias { static constexpr int kCol = C::FC ? 0 : C::F; };
 // 10 per-unit values -> TMEM columns col0 + unit as 3xTF32 hi (at t_hi) / lo (at t_lo)   (col0 = column of unit 0)
 __device__ __forceinline__ void st_split10(const UnitMap& um, uint32_t t_hi, uint32_t t_lo, int col0, const float* v) {
   chunks10(um, [&](auto k0c, auto ncc, int ub) {
@@ -278,10 +294,35 @@ __device__ __forceinline__ void flush_dw1(const l2o_bwd_args& a, uint32_t tl, in
   }
 }
 
+// fc nets, layer-1 pass: the chain runs on the layer-2 resources; X slots = [h1p 0..19 | fc outputs e 20..39 | one 40]
+template <class C>
+__device__ __forceinline__ void flush_dwfc(const l2o_bwd_args& a, uint32_t tl, int c) {
+  const int m = c - kYZ16;
+  const int col = (m & 3) * kH + (m >> 2);
+#pragma unroll
+  for (int k4 = 0; k4 < 48 / 4; ++k4) {
+    float v[4];
+    tcb::tmem_ld4(tl + cW2 + 4 * k4, v);
+    if (m >= 0 && m < kN) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 4 * k4 + e;
+        int idx = -1;
+        if (k < kH) idx = C::O_W1 + (C::F + k) * C::G1 + col;          // lstm_1/w_gates rows: inputs (F) first, then h1
+        else if (k < 2 * kH) idx = C::O_W1 + (k - kH) * C::G1 + col;
+        else if (k == kX2One) idx = C::O_B1 + col;
+        if (idx >= 0) atomicAdd(&a.dtheta[idx], (double)v[e]);
+      }
+    }
+  }
+}
+
 // =====================================================================================================================
 // layer-2 workers: output layer + layer-2 LSTM backward
 // =====================================================================================================================
-template <class C>
+// EXPORT (single-chain pass A of fc nets): dX2(t)[h1n], which the layer-1 threads of the pipelined kernel read straight
+// from TMEM, goes to a.scratch [T][n][20] for the layer-1 pass.
+template <class C, bool EXPORT>
 __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt& rt, SmemB2& S, uint32_t tmem_base, int warp,
                                               int lane) {
   const int half = (warp >> 2) & 1;   // run-time: both halves share one instruction stream
@@ -300,6 +341,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
   int pi = 0;
   const bool prof = (half == 0 && q == 0 && lane == 0);
   (void)pi; (void)prof;
+  int64_t exp_row = -1;   // EXPORT: scratch row (t * n + i) of the step whose dX2 is in flight, -1 = inactive lane
   float acc_wo[kNU], acc_bo = 0.f;
 #pragma unroll
   for (int k = 0; k < kNU; ++k) acc_wo[k] = 0.f;
@@ -319,7 +361,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
       const float* ck = a.ckpt + (int64_t)t * slot;
       // ---- P0: checkpoint rows (h1n(t) IS the checkpointed h1 of slot t+1), A2 = [0 | 0..1..0 | h1n | h2p] --------
       float c2p[kNU];
-      float g_t = 0.f;
+      float g_t = 0.f, dtanh = 1.0f;
       if (prof) { L2O_PROF2(0, pi, 0); ++pi; }
       {
         float h1n[kNU], h2p[kNU];
@@ -337,11 +379,20 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
         }
         if (imit && act) lam = (a.delta_seq[(int64_t)t * n + i] - a.labels[(int64_t)t * n + i]) * inv_nt;
         if (!imit && act) g_t = a.g_rec[(int64_t)t * n + i];   // consumed at the end of the step (suffix sum)
+        if (rt.tanh_output && act) {   // delta = scale tanh(y): the forward pass's recorded delta gives tanh' without y
+          const float th = a.delta_seq[(int64_t)t * n + i] / rt.scale;
+          dtanh = fmaf(-th, th, 1.0f);
+        }
         if (have_prev) {  // dX2 of the previous step: the h2p columns are this chain's carry, and the aliased
           mbar_wait(&S.x_done[0], px);  // dZ2-lo / A2 region becomes writable
           px ^= 1;
           tc_fence_after();
           if (t != T - 1) ld10(um, tX, kA2H2P, dh2c);
+          if constexpr (EXPORT) {
+            float v[kNU];
+            ld10(um, tX, kA2H1N, v);
+            if (exp_row >= 0) store10(um, a.scratch + exp_row * kH, v);
+          }
         }
         if (prof) { L2O_PROF2(0, pi, 1); ++pi; }
         if (t == T - 1) {
@@ -352,7 +403,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
         st_split10(um, tRh, tRl, kA2H2P, h2p);
         if (half == 1) {  // constant columns 0..7: zero-weight rows + the bias 1 at 4+F
           float one[4] = {0.f, 0.f, 0.f, 0.f};
-          one[C::F] = 1.0f;
+          one[Bias<C>::kCol] = 1.0f;
           tmem_st4(tRh, 0.f, 0.f, 0.f, 0.f);
           tmem_st4(tRl, 0.f, 0.f, 0.f, 0.f);
           tmem_st4(tRh + kA2One, one[0], one[1], one[2], one[3]);
@@ -379,7 +430,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
         stage_units10(um, yh, yl, c, kX2H2P, h2p);
       }
       // ---- layer-2 gates, output layer, layer-2 backward: dZ2 -> TMEM (hi in place, lo over A2) + bf16 staging ------
-      const float dy = rt.scale * lam;
+      const float dy = rt.scale * lam * dtanh;
       if (half == 1) acc_bo += dy;
       mbar_wait(&S.z_done[0], pz);
       pz ^= 1;
@@ -405,7 +456,18 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
       mbar_arrive(&S.dz_ready[0]);
       if (prof) { L2O_PROF2(0, pi, 4); ++pi; }
       have_prev = true;
+      if constexpr (EXPORT) exp_row = act ? (int64_t)t * n + i : -1;
       lam += g_t;
+    }
+  }
+  if constexpr (EXPORT) {   // dX2 of the very last step
+    if (have_prev) {
+      mbar_wait(&S.x_done[0], px);
+      px ^= 1;
+      tc_fence_after();
+      float v[kNU];
+      ld10(um, tX, kA2H1N, v);
+      if (exp_row >= 0) store10(um, a.scratch + exp_row * kH, v);
     }
   }
   // ---- flush: output-layer gradient from registers -------------------------------------------------------------------
@@ -414,8 +476,7 @@ __device__ __forceinline__ void layer2_worker(const l2o_bwd_args& a, const NetRt
     float v = acc_wo[k];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int unit = (k < 4 ? um.u0 : (k < 8 ? um.u1 - 4 : um.u2 - 8)) + k;   // array index -> hidden unit
-    if (lane == 0) atomicAdd(&a.dtheta[C::O_WO + unit], (double)v);
+    if (lane == 0) atomicAdd(&a.dtheta[C::O_WO + unit_of(um, k)], (double)v);
   }
   if (half == 1) {
     float v = acc_bo;
@@ -567,7 +628,176 @@ __device__ __forceinline__ void layer1_worker(const l2o_bwd_args& a, const NetRt
   if (half == 0) flush_dw1<C>(a, tl, c);
 }
 
+
+// =====================================================================================================================
+// fc(20) nets (RNNProp, DM/networks.py:279-300), layer-1 pass.  Layer 1 of these nets has the SAME operand geometry as
+// layer 2 (K = 48: [h1p | e | 1 | 0], dX N = 48, dW^T N = 48), so the chain runs on the layer-2 columns, staging buffers,
+// barriers and issuer branch, with its own weight image in the B2'/T2 slots.  dX2(t)[h1n] comes from a.scratch (pass
+// A).  The fc layer's own gradient (dWin [2 x 20], dbin [20]) needs de = dX1[20..39], which arrives one step late with
+// the chain carry: it is folded into per-thread fp32 sums then (a thread owns the same 10 units of e as of h1).
+// =====================================================================================================================
 template <class C>
+__device__ __forceinline__ void fc1_worker(const l2o_bwd_args& a, const NetRt& rt, SmemB2& S, uint32_t tmem_base, int warp,
+                                           int lane, const float* __restrict__ win) {
+  static_assert(C::FC && C::NIN == 2 && C::F == kH, "fc(2 -> 20) preprocessing");
+  const int half = (warp >> 2) & 1;
+  const UnitMap um(half);
+  const int q = warp & 3;
+  const int c = q * 32 + lane;
+  const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+  const uint32_t tZ = tl + cZ2, tRh = tl + cR2, tRl = tl + cR2 + kA2Cols, tDl = tl + cR2, tX = tl + cX2;
+  const uint32_t yh = smem_u32(S.y2h), yl = smem_u32(S.y2l);
+  constexpr int kAE = kH, kAOne = 2 * kH;   // A columns / X slots of e and of the constant 1
+  const int T = a.T;
+  const int64_t n = a.n, slot = n * C::SF, ntiles = (n + 127) / 128;
+  uint32_t pz = 0, px = 0, pw = 0;
+  bool have_prev = false;
+  float aw0[kNU], aw1[kNU], ab[kNU], ep[kNU];
+#pragma unroll
+  for (int k = 0; k < kNU; ++k) { aw0[k] = 0.f; aw1[k] = 0.f; ab[k] = 0.f; ep[k] = 0.f; }
+  float r0p = 0.f, r1p = 0.f;   // the inputs of the step whose de is still in flight
+  if (half == 0) {
+#pragma unroll
+    for (int k = 0; k < 48 / 4; ++k) tmem_st4(tl + cW2 + 4 * k, 0.f, 0.f, 0.f, 0.f);
+    tc_wait_st();
+  }
+  auto take_de = [&]() {   // da = de * elu'(a);  dWin += [m~, g~]^T da, dbin += da
+    float de[kNU];
+    ld10(um, tX, kAE, de);
+#pragma unroll
+    for (int k = 0; k < kNU; ++k) {
+      const float da = de[k] * ep[k];
+      aw0[k] = fmaf(r0p, da, aw0[k]);
+      aw1[k] = fmaf(r1p, da, aw1[k]);
+      ab[k] += da;
+    }
+  };
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t i = tile * 128 + c;
+    const bool act = i < n;
+    float dc1[kNU], dh1[kNU];
+#pragma unroll
+    for (int k = 0; k < kNU; ++k) { dc1[k] = 0.f; dh1[k] = 0.f; }
+    for (int t = T - 1; t >= 0; --t) {
+      const float* ck = a.ckpt + (int64_t)t * slot;
+      float c1p[kNU], dimp[kNU];
+      {
+        float h1p[kNU], e[kNU];
+#pragma unroll
+        for (int k = 0; k < kNU; ++k) { h1p[k] = 0.f; c1p[k] = 0.f; dimp[k] = 0.f; }
+        float raw0 = 0.f, raw1 = 0.f;
+        if (act) {
+          load10(um, ck + i * kH, h1p);
+          load10(um, ck + (n + i) * kH, c1p);
+          load10(um, a.scratch + ((int64_t)t * n + i) * kH, dimp);
+          raw0 = a.in_seq[((int64_t)t * 2) * n + i];
+          raw1 = a.in_seq[((int64_t)t * 2 + 1) * n + i];
+          if (t > 0) {
+            const float* nk = ck - slot;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + i * kH + um.u2));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nk + (n + i) * kH + um.u2));
+          }
+        }
+        if (have_prev) {  // dX1 of the previous step: chain carry + the fc layer's gradient of that step
+          mbar_wait(&S.x_done[0], px);
+          px ^= 1;
+          tc_fence_after();
+          take_de();
+          if (t != T - 1) ld10(um, tX, 0, dh1);
+        }
+        if (t == T - 1) {
+#pragma unroll
+          for (int k = 0; k < kNU; ++k) dh1[k] = 0.f;
+        }
+        // e = elu([m~, g~] Win + bin) for this thread's units, as the forward kernel computes it (cwlstm_tc.cuh)
+#pragma unroll
+        for (int k = 0; k < kNU; ++k) {
+          const int u = unit_of(um, k);
+          const float av = fmaf(raw1, win[kH + u], fmaf(raw0, win[u], win[2 * kH + u]));
+          const float em = ex2_approx(kLog2e * av) - 1.0f;
+          const float et = av * fmaf(av, fmaf(av, fmaf(av, 1.0f / 24.0f, 1.0f / 6.0f), 0.5f), 1.0f);
+          e[k] = av > 0.f ? av : (av > -0.0625f ? et : em);
+          ep[k] = av > 0.f ? 1.0f : e[k] + 1.0f;   // elu' = exp(a) on the negative side
+        }
+        r0p = raw0;
+        r1p = raw1;
+        st_split10(um, tRh, tRl, 0, h1p);
+        st_split10(um, tRh, tRl, kAE, e);
+        if (half == 1) {
+          tmem_st4(tRh + kAOne, 1.0f, 0.f, 0.f, 0.f);
+          tmem_st4(tRl + kAOne, 0.f, 0.f, 0.f, 0.f);
+          tmem_st4(tRh + kAOne + 4, 0.f, 0.f, 0.f, 0.f);
+          tmem_st4(tRl + kAOne + 4, 0.f, 0.f, 0.f, 0.f);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&S.a_ready[0]);
+        if (have_prev) {
+          mbar_wait(&S.w_done[0], pw);
+          pw ^= 1;
+          if (t == T - 1 && half == 0) {
+            tc_fence_after();
+            flush_dwfc<C>(a, tl, c);
+            tc_fence_before();
+            mbar_arrive(&S.flushed[0]);
+          }
+        }
+        stage_units10(um, yh, yl, c, 0, h1p);
+        stage_units10(um, yh, yl, c, kAE, e);
+      }
+#pragma unroll
+      for (int k = 0; k < kNU; ++k) dh1[k] += dimp[k];   // dX2(t)[h1n], handed over by pass A
+      mbar_wait(&S.z_done[0], pz);
+      pz ^= 1;
+      tc_fence_after();
+      chunks10(um, [&](auto k0c, auto ncc, int ub) {
+        L2O_CHUNK(K0, NC, k0c, ncc);
+        float z[4 * NC];
+        tmem_ldn<4 * NC>(tZ + 4 * ub, z);
+        tc_wait_ld();
+        chunk_bwd<NC>(z, c1p + K0, dh1 + K0, dc1 + K0, nullptr);
+        put_dz<NC>(tZ, tDl, 4 * ub, z);
+#pragma unroll
+        for (int g8 = 0; g8 < NC / 2; ++g8) stage16<8>(yh, yl, c, kYZ16 + 4 * ub + 8 * g8, z + 8 * g8);
+      });
+      fence_proxy_async();
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&S.dz_ready[0]);
+      have_prev = true;
+    }
+  }
+  if (have_prev) {   // de of the very last step, then the dW1^T accumulators of the last tile
+    mbar_wait(&S.x_done[0], px);
+    px ^= 1;
+    tc_fence_after();
+    take_de();
+    mbar_wait(&S.w_done[0], pw);
+    pw ^= 1;
+  }
+#pragma unroll
+  for (int k = 0; k < kNU; ++k) {
+    float v0 = aw0[k], v1 = aw1[k], vb = ab[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      vb += __shfl_xor_sync(0xffffffffu, vb, o);
+    }
+    if (lane == 0) {
+      const int u = unit_of(um, k);
+      atomicAdd(&a.dtheta[C::O_WIN + u], (double)v0);
+      atomicAdd(&a.dtheta[C::O_WIN + C::F + u], (double)v1);
+      atomicAdd(&a.dtheta[C::O_BIN + u], (double)vb);
+    }
+  }
+  tc_fence_after();
+  if (half == 0) flush_dwfc<C>(a, tl, c);
+}
+
+// MODE 0: both chains, layer-pipelined.  MODE 1 / 2 (fc nets): the layer-2 chain alone (exporting dX2[h1n]) / the fc layer-1
+// chain alone on the layer-2 resources; warps 8-15 idle.
+template <class C, int MODE>
 __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args a, NetRt rt, const float* __restrict__ img) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   SmemB2& S = *reinterpret_cast<SmemB2*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -581,6 +811,9 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
     for (int k = threadIdx.x; k < 4 * kY16Elems / 2; k += blockDim.x) y[k] = 0u;
   }
   if (threadIdx.x < kH) S.wo[threadIdx.x] = a.theta[C::O_WO + threadIdx.x];
+  if constexpr (C::FC) {
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 3 * kH) S.win[threadIdx.x - 64] = a.theta[C::O_WIN + threadIdx.x - 64];
+  }
   __syncthreads();
   for (int cc = threadIdx.x; cc < 128; cc += blockDim.x)
     *reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(S.y2h) + y16_off(cc, kX2One)) = 0x3F80u;
@@ -615,9 +848,17 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
   const uint32_t tmem_base = S.tmem_slot;
 
   if (warp < kIssuerWarp) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs2));
-    if (warp < 8) layer2_worker<C>(a, rt, S, tmem_base, warp, lane);
-    else layer1_worker<C>(a, rt, S, tmem_base, warp, lane);
+    if constexpr (MODE == 0) {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs2));
+      if (warp < 8) layer2_worker<C, false>(a, rt, S, tmem_base, warp, lane);
+      else layer1_worker<C>(a, rt, S, tmem_base, warp, lane);
+    } else if (warp >= 8) {   // single-chain passes: the other chain's warps hand their registers to the workers
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(24));
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSoloRegs2));
+      if constexpr (MODE == 1) layer2_worker<C, true>(a, rt, S, tmem_base, warp, lane);
+      else if constexpr (C::FC) fc1_worker<C>(a, rt, S, tmem_base, warp, lane, S.win);
+    }
   } else if (warp > kIssuerWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kIssRegs2));
   } else {
@@ -651,9 +892,10 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
     uint32_t pA[2] = {0, 0}, pD[2] = {0, 0}, pF[2] = {0, 0}, pT = 0;
     int pi = 0;
     (void)pi;
+    if (MODE != 0) nA[1] = nD[1] = total;               // single-chain passes: chain 1 has nothing to do
     while (nD[0] < total || nD[1] < total) {
 #pragma unroll
-      for (int l = 0; l < 2; ++l) {
+      for (int l = 0; l < (MODE == 0 ? 2 : 1); ++l) {
         // A(t): gate recompute Z_l = A_l . B_l'
         if (nA[l] < total && nA[l] == nD[l] && mbar_test(&S.a_ready[l], pA[l])) {
           pA[l] ^= 1;
@@ -684,8 +926,8 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
         // dW_l^T batch right behind it: the layer's own next request (Z of step t-1) comes a whole P0 later, by which
         // time the 24 SS-mode MMAs have drained
         if (nD[l] < nA[l] && mbar_test(&S.dz_ready[l], pD[l]) &&
-            (l == 1 || nD[0] == 0 || mbar_test(&S.x2_taken, pT))) {
-          if (l == 0 && nD[0] > 0) pT ^= 1;
+            (MODE != 0 || l == 1 || nD[0] == 0 || mbar_test(&S.x2_taken, pT))) {
+          if (MODE == 0 && l == 0 && nD[0] > 0) pT ^= 1;
           pD[l] ^= 1;
           // first step of a tile: its dW batch OVERWRITES the accumulators.  The previous tile's values were drained
           // by the workers before they signalled this step's a_ready, so the handshake never blocks here.
@@ -742,12 +984,23 @@ __global__ void __launch_bounds__(kThreads2, 1) unroll_bwd2_kernel(l2o_bwd_args 
 template <class C>
 int tc_launch_bwd2(const NetRt& rt, const l2o_bwd_args& a, float* img, cudaStream_t st, int sms) {
   tc::prep_weights_kernel<C><<<8, 256, 0, st>>>(a.theta, img, 1);
-  auto k = tcb2::unroll_bwd2_kernel<C>;
   const size_t smem = sizeof(tcb2::SmemB2) + 1024;
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
   const int64_t ntiles = (a.n + 127) / 128;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  k<<<grid, tcb2::kThreads2, smem, st>>>(a, rt, img);
+  if constexpr (C::FC) {
+    // two single-chain passes over time (layer 2, then layer 1 fed by a.scratch): both chains' K = 48 images plus both
+    // staging buffers exceed the shared memory and TMEM of one CTA
+    auto ka = tcb2::unroll_bwd2_kernel<C, 1>;
+    auto kb = tcb2::unroll_bwd2_kernel<C, 2>;
+    if (cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
+    if (cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
+    ka<<<grid, tcb2::kThreads2, smem, st>>>(a, rt, img);
+    kb<<<grid, tcb2::kThreads2, smem, st>>>(a, rt, img + tc::kImgAllFloats);
+  } else {
+    auto k = tcb2::unroll_bwd2_kernel<C, 0>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
+    k<<<grid, tcb2::kThreads2, smem, st>>>(a, rt, img);
+  }
   return cudaGetLastError() == cudaSuccess ? L2O_OK : L2O_E_CUDA;
 }
 

@@ -118,7 +118,9 @@ int l2o_workspace_bytes(l2o_handle h, int64_t n, int32_t T, size_t* fwd_bytes, s
   const size_t grec = (size_t)(T + 1) * (size_t)n * sizeof(float);
   const size_t feat = h->desc.n_in == 2 ? (size_t)T * 2 * (size_t)n * sizeof(float) : 0;
   if (fwd_bytes) *fwd_bytes = arena + ckpt + grec + feat;
-  if (bwd_bytes) *bwd_bytes = ckpt + grec + feat + (size_t)h->n_theta * sizeof(double);
+  // fc(20) nets: + the recorded deltas and the [T][n][20] hand-over buffer of the two-pass tensor-core BPTT (both optional)
+  const size_t fc_extra = h->cfg == 2 ? (size_t)T * (size_t)n * (1 + 20) * sizeof(float) : 0;
+  if (bwd_bytes) *bwd_bytes = ckpt + grec + feat + fc_extra + (size_t)h->n_theta * sizeof(double);
   return L2O_OK;
 }
 

@@ -11,9 +11,10 @@
 
 namespace l2o {
 // forward / step: LSTM-20x2 with identity / LogAndSign preprocessing (cfg 0, 1) and RNNProp's fc(2->20)+ELU net (cfg 2);
-// BPTT: cfg 0, 1 (RNNProp's K = 48 weight images do not fit next to the dW staging)
+// BPTT: cfg 0, 1 layer-pipelined in one kernel; cfg 2 as two single-chain passes (its K = 48 layer-1 operands do not fit next
+// to layer 2's in shared memory / TMEM) with a caller-provided hand-over buffer
 bool tc_supported(int cfg) { return cfg == 0 || cfg == 1 || cfg == 2; }
-static bool tc_bwd_supported(int cfg) { return cfg == 0 || cfg == 1; }
+static bool tc_bwd_supported(int cfg) { return cfg == 0 || cfg == 1 || cfg == 2; }
 bool tc_fwd_ok(const l2o_net* h, const l2o_unroll_args& a) {
   if (a.opt_kind == L2O_OPT_QUADRATIC_BATCH) return false;  // grouped optimizees exchange x: exact-fp32 engine only
   if (h->cfg == 2) return true;                             // fused Adam-feature mode (m, v) or given (m~, g~) rows
@@ -27,7 +28,7 @@ static bool tc_auto_env() {
 bool tc_auto_default() { return tc_auto_env(); }
 bool tc_bwd_auto_default() { return tc_auto_env(); }  // parity-green on the B200 (tests/test_tc_gpu.py)
 
-// Weight-image buffers (97 KB each) are recycled through a process-wide free list and never cudaFree'd: a handle may
+// Weight-image buffers (2 x 97 KB each) are recycled through a process-wide free list and never cudaFree'd: a handle may
 // be destroyed (Python GC) while ANOTHER program is capturing a CUDA graph, and cudaFree during a capture invalidates it.
 namespace {
 struct ImgPool {
@@ -63,7 +64,7 @@ static int ensure_image(l2o_net* h) {
           break;
         }
     }
-    if (h->tc_img == nullptr) L2O_CUDA_TRY(cudaMalloc(&h->tc_img, tc::kImgAllBytes));
+    if (h->tc_img == nullptr) L2O_CUDA_TRY(cudaMalloc(&h->tc_img, 2 * tc::kImgAllBytes));   // fc nets: one BPTT image per pass
     h->tc_img_dev = dev;
     h->tc_img_mode = -1;
   }
@@ -73,7 +74,9 @@ static int ensure_image(l2o_net* h) {
 bool tc_bwd_ok(const l2o_net* h, const l2o_bwd_args& a) {
   // meta-loss mode (lambda suffix sums of g_rec) or imitation mode with the forward pass's recorded deltas
   const bool mode_ok = a.labels ? (a.delta_seq != nullptr && a.n_total > 0) : a.g_rec != nullptr;
-  return tc_bwd_supported(h->cfg) && mode_ok && !h->rt.tanh_output;
+  if (h->cfg == 2 && (a.scratch == nullptr || a.labels != nullptr)) return false;   // fc nets: meta-loss mode with a hand-over buffer
+  if (h->rt.tanh_output && a.delta_seq == nullptr) return false;   // tanh' comes from the recorded deltas
+  return tc_bwd_supported(h->cfg) && mode_ok;
 }
 
 int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {
@@ -92,8 +95,9 @@ int tc_unroll_bwd(l2o_net* h, const l2o_bwd_args& a, cudaStream_t st) {
   } else {
     if (h->cfg == 0) rc = tc_launch_bwd2<Cfg<L2O_PRE_IDENTITY, 1, 1, 20, 20>>(h->rt, a, h->tc_img, st, sms);
     if (h->cfg == 1) rc = tc_launch_bwd2<Cfg<L2O_PRE_LOGSIGN, 1, 2, 20, 20>>(h->rt, a, h->tc_img, st, sms);
+    if (h->cfg == 2) rc = tc_launch_bwd2<Cfg<L2O_PRE_FC, 2, 20, 20, 20>>(h->rt, a, h->tc_img, st, sms);
   }
-  if (rc == L2O_OK) count_launch(2);
+  if (rc == L2O_OK) count_launch(h->cfg == 2 ? 3 : 2);
   h->tc_img_mode = 1;
   if (rc == L2O_E_CUDA) return set_cuda_error(cudaGetLastError(), "tc_unroll_bwd launch");
   return rc;

@@ -138,7 +138,11 @@ class NetHandle:
         a.opt_group = opt_group
         _lib.check(_lib.lib().l2o_unroll_fwd(self._h, C.byref(a), _stream()), "l2o_unroll_fwd")
 
-    def unroll_bwd(self, theta, n, T, in_seq, ckpt, dtheta, *, g_rec=None, labels=None, n_total=0, delta_seq=None):
+    def unroll_bwd(self, theta, n, T, in_seq, ckpt, dtheta, *, g_rec=None, labels=None, n_total=0, delta_seq=None,
+                   scratch=None):
+        """BPTT over the T checkpoint slots.  ``scratch`` ([T, n, 20] floats) lets fc(20) nets (RNNProp) run on the
+        tensor-core engine; ``delta_seq`` (the deltas the forward pass recorded) is what a tanh-output net's
+        tensor-core BPTT differentiates the output layer with."""
         a = BwdArgs()
         a.n, a.T = n, T
         a.theta = _ptr(theta, name="theta")
@@ -147,6 +151,9 @@ class NetHandle:
         a.n_total = n_total
         a.dtheta = _ptr(dtheta, torch.float64, "dtheta")
         a.delta_seq = _ptr(delta_seq, name="delta_seq")
+        if scratch is not None and scratch.numel() < T * n * 20:
+            raise L2OError(f"scratch has {scratch.numel()} floats, the fc-net BPTT needs T*n*20 = {T * n * 20}")
+        a.scratch = _ptr(scratch, name="scratch")
         _lib.check(_lib.lib().l2o_unroll_bwd(self._h, C.byref(a), _stream()), "l2o_unroll_bwd")
 
 

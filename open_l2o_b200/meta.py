@@ -218,6 +218,14 @@ class _Program(object):
                 r.v = torch.zeros(r.n, device=self.device)
                 r.m_work, r.v_work = torch.zeros_like(r.m), torch.zeros_like(r.v)
                 r.feat_rec = torch.zeros(T, 2, r.n, device=self.device)
+            # what the tensor-core BPTT of a tanh-output / fc(20) net (RNNProp) needs on top: the recorded deltas
+            # (tanh' of the output layer) and the hand-over buffer between its layer-2 and layer-1 pass
+            r.delta_rec = r.bwd_scratch = None
+            h = r.net.handle
+            if getattr(r.net, "tanh_output", False) and isinstance(h, _engine.NetHandle):
+                r.delta_rec = torch.zeros(T, r.n, device=self.device)
+            if h.n_in == 2 and isinstance(h, _engine.NetHandle) and tuple(h.layers) == (20, 20):
+                r.bwd_scratch = torch.zeros(T, r.n, 20, device=self.device)
         self.fx_buf = torch.zeros(T + 1, dtype=torch.float64, device=self.device)
 
     def reset_x(self):
@@ -354,6 +362,8 @@ class _Program(object):
             r.v_work.copy_(r.v)
             kw = dict(m=r.m_work, v=r.v_work, beta1=self.opt.beta1, beta2=self.opt.beta2, step0=step0,
                       feat_rec=r.feat_rec)
+        if train and r.delta_rec is not None:
+            kw["delta_seq"] = r.delta_rec
         h.unroll_fwd(r.net.theta, r.n, T, work_state, opt_kind=_engine.OPT_KINDS[f.kind],
                      opt_a=self.const_vals[f.a].reshape(-1), opt_b=self.const_vals[f.b].reshape(-1),
                      opt_alpha=f.alpha, opt_fscale=f.fscale, x=r.x_work, ckpt=r.ckpt if train else None,
@@ -382,6 +392,8 @@ class _Program(object):
                 if h.n_in == 2:
                     kw = dict(m=r.m_work, v=r.v_work, beta1=self.opt.beta1, beta2=self.opt.beta2,
                               step_ptr=self.step_dev, t_offset=t, feat_out=r.feat_rec[t])
+                if train and r.delta_rec is not None:
+                    kw["delta"] = r.delta_rec[t]
                 # theta is constant inside an unroll: the weight image built at t = 0 serves every later step (runs that
                 # share a net share its handle, so only the first run of step 0 rebuilds)
                 h.step(r.net.theta, r.g_rec[t], r.ckpt[t * slot:(t + 1) * slot], r.ckpt[(t + 1) * slot:(t + 2) * slot],
@@ -414,8 +426,18 @@ class _Program(object):
             for r in self.runs:
                 h = r.net.handle
                 in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
-                h.unroll_bwd(r.net.theta, r.n, self.T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec)
+                h.unroll_bwd(r.net.theta, r.n, self.T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec,
+                             **self._bwd_extra(r))
         return fx
+
+    @staticmethod
+    def _bwd_extra(r):
+        kw = {}
+        if r.delta_rec is not None:
+            kw["delta_seq"] = r.delta_rec
+        if r.bwd_scratch is not None:
+            kw["scratch"] = r.bwd_scratch
+        return kw
 
     def _graph_eligible(self):
         # RNNProp's bias-correction exponent p = step0 + t is read from a device scalar (self.step_dev), so the graph
@@ -489,7 +511,8 @@ class _Program(object):
                 for r in self.runs:
                     h = r.net.handle
                     in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
-                    h.unroll_bwd(r.net.theta, r.n, T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec)
+                    h.unroll_bwd(r.net.theta, r.n, T, in_seq, r.ckpt, self.dtheta[r.key], g_rec=r.g_rec,
+                                 **self._bwd_extra(r))
         else:
             fx = self._run_external(train, step0)
         if train:

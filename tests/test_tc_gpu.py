@@ -252,3 +252,49 @@ def test_tc_rnnprop_fused_unroll_matches_ffma():
         outs[eng] = (x, arena, fx, g_rec, feat, m, v, ckpt)
     for u, w in zip(outs[ENGINE_TC], outs[ENGINE_FFMA]):
         assert rel_err(u, w) <= REL_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,T", [(148 * 128 + 77, 5), (2 * 148 * 128 + 300, 20), (100, 3)])
+def test_tc_rnnprop_bptt_two_pass_matches_ffma(n, T):
+    """RNNProp (fc(20) + ELU, tanh output) BPTT on the tcgen05 engine — layer-2 pass, hand-over buffer, layer-1 pass
+    with the fc layer's own gradient — against the exact-fp32 engine on the same checkpoints, features and deltas
+    (DM/networks.py:279-300, DM/meta.py:319-376).  Several tiles per CTA and a ragged tail."""
+    from open_l2o_b200.engine import ENGINE_FFMA, ENGINE_TC, OPT_KINDS
+    spec = SPECS["rnnprop"]
+    gen = torch.Generator().manual_seed(31)
+    theta = _theta(spec, gain=0.3).to(DEV)
+    a, b, x0 = (torch.randn(n, generator=gen).to(DEV) for _ in range(3))
+    h = make_handle(spec)
+    h.set_engine(ENGINE_FFMA)
+    arena = h.new_state(n, DEV)
+    x = x0.clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    g_rec = torch.empty(T + 1, n, device=DEV)
+    feat = torch.empty(T, 2, n, device=DEV)
+    dseq = torch.empty(T, n, device=DEV)
+    ckpt = torch.zeros((T + 1) * h.state_floats * n, device=DEV)
+    h.unroll_fwd(theta, n, T, arena, opt_kind=OPT_KINDS["rastrigin_sep"], opt_a=a, opt_b=b, opt_alpha=10.0,
+                 opt_fscale=1.0 / n, x=x, ckpt=ckpt, m=m, v=v, beta1=0.95, beta2=0.95, step0=1, g_rec=g_rec,
+                 feat_rec=feat, delta_seq=dseq)
+    outs = {}
+    for eng in (ENGINE_FFMA, ENGINE_TC):
+        h.set_engine(eng)
+        d = torch.zeros(h.n_theta, dtype=torch.float64, device=DEV)
+        kw = {}
+        if eng == ENGINE_TC:
+            kw = dict(delta_seq=dseq, scratch=torch.empty(T, n, 20, device=DEV))
+        h.unroll_bwd(theta, n, T, feat, ckpt, d, g_rec=g_rec, **kw)
+        torch.cuda.synchronize()
+        outs[eng] = d
+    ref = outs[ENGINE_FFMA]
+    assert float(ref.abs().max()) > 0
+    # every block of theta on its own scale (the fc layer's gradient is orders of magnitude below the LSTM's)
+    off = 0
+    for name, cnt in (("fc_w", 40), ("fc_b", 20), ("w1", 40 * 80), ("b1", 80), ("w2", 40 * 80), ("b2", 80), ("wo", 20), ("bo", 1)):
+        u, w = outs[ENGINE_TC][off:off + cnt], ref[off:off + cnt]
+        assert rel_err(u, w) <= 2e-5, (name, rel_err(u, w))
+        off += cnt
+    assert off == h.n_theta
+    with pytest.raises(Exception):   # without the hand-over buffer the tcgen05 engine refuses an fc net
+        h.unroll_bwd(theta, n, T, feat, ckpt, torch.zeros_like(ref), g_rec=g_rec, delta_seq=dseq)
