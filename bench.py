@@ -190,7 +190,7 @@ def external_roofline(prog, netkind, T, t_unroll):
     t_step = timed(step_once, 2 * T)
     dth = torch.zeros_like(prog.dtheta[r.key])
     in_seq = r.feat_rec if h.n_in == 2 else r.g_rec
-    t_bwd = timed(lambda: h.unroll_bwd(r.net.theta, n, T, in_seq, r.ckpt, dth, g_rec=r.g_rec), 3)
+    t_bwd = timed(lambda: h.unroll_bwd(r.net.theta, n, T, in_seq, r.ckpt, dth, g_rec=r.g_rec, **prog._bwd_extra(r)), 3)
     sb, bb = STEP_BYTES[netkind], BWD_BYTES[netkind]
     ach = sb * n / t_step / 1e9
     ws = (T + 1) * slot * 4

@@ -74,7 +74,7 @@ static int ensure_image(l2o_net* h) {
 bool tc_bwd_ok(const l2o_net* h, const l2o_bwd_args& a) {
   // meta-loss mode (lambda suffix sums of g_rec) or imitation mode with the forward pass's recorded deltas
   const bool mode_ok = a.labels ? (a.delta_seq != nullptr && a.n_total > 0) : a.g_rec != nullptr;
-  if (h->cfg == 2 && (a.scratch == nullptr || a.labels != nullptr)) return false;   // fc nets: meta-loss mode with a hand-over buffer
+  if (h->cfg == 2 && a.scratch == nullptr) return false;   // fc nets: two passes with a caller-provided hand-over buffer
   if (h->rt.tanh_output && a.delta_seq == nullptr) return false;   // tanh' comes from the recorded deltas
   return tc_bwd_supported(h->cfg) && mode_ok;
 }

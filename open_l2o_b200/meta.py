@@ -580,7 +580,8 @@ class _MtTask(object):
                       lab=Placeholder("mt{}_label_subset{}".format(index, len(self.subsets))))
             if h.n_in == 2:   # RNNProp: the task carries its own Adam moments (DM/meta_rnnprop_train.py:469-486)
                 sb.update(m=torch.zeros(r.n, device=prog.device), v=torch.zeros(r.n, device=prog.device),
-                          feat=torch.zeros(T, 2, r.n, device=prog.device))
+                          feat=torch.zeros(T, 2, r.n, device=prog.device),
+                          scratch=r.bwd_scratch)   # hand-over buffer of the two-pass tensor-core BPTT (shared with the run)
             self.subsets.append(sb)
         self.n_total = sum(sb["n"] for sb in self.subsets)
         self.adam = {k: dict(m=torch.zeros_like(net.theta), v=torch.zeros_like(net.theta), k=0)
@@ -618,10 +619,11 @@ class _MtTask(object):
                 mw, vw = sb["m"].clone(), sb["v"].clone()
                 h.unroll_fwd(r.net.theta, n, T, work, in_seq=inp, ckpt=sb["ckpt"] if train else None, labels=lab,
                              imit_loss=self.il, n_total=self.n_total, m=mw, v=vw, beta1=prog.opt.beta1,
-                             beta2=prog.opt.beta2, step0=step0, feat_rec=sb["feat"])
+                             beta2=prog.opt.beta2, step0=step0, feat_rec=sb["feat"],
+                             delta_seq=sb["dseq"] if train else None)
                 if train:
                     h.unroll_bwd(r.net.theta, n, T, sb["feat"], sb["ckpt"], prog.dtheta[r.key], labels=lab,
-                                 n_total=self.n_total)
+                                 n_total=self.n_total, delta_seq=sb["dseq"], scratch=sb["scratch"])
                 finals.append((work, mw, vw))
                 continue
             h.unroll_fwd(r.net.theta, n, T, work, in_seq=inp, ckpt=sb["ckpt"] if train else None, labels=lab,
