@@ -24,7 +24,7 @@ constexpr int kTiles = 2;                    // coordinate tiles per CTA
 constexpr int kTileCoords = 128 * kTiles;    // coordinates per CTA pass
 constexpr int kEpiThreads = 256 * kTiles;    // a thread PAIR per coordinate (hidden units 0..11 | 12..19)
 constexpr int kThreads = kEpiThreads + 128;  // + the warpgroup that holds the MMA / alloc warp (3 idle warps)
-constexpr int kFwdEpiRegs = 112, kFwdIssuerRegs = 32;  // setmaxnreg targets (pool: 640 threads x 96)
+constexpr int kFwdEpiRegs = 104, kFwdIssuerRegs = 64;  // setmaxnreg targets; 512 x 104 + 128 x 64 = the launch allocation 640 x 96 (no spare registers on the SM)
 constexpr int kH = 20;
 constexpr int kN = 4 * kH;                   // 80 gate columns
 constexpr int kXC = 4;                       // feature chunk: cols [0, kXC): features, then the constant 1
@@ -58,13 +58,35 @@ struct Geo {
   static constexpr int K1 = FC ? 48 : kK1;
   static constexpr int K2 = 48;
   static constexpr int A2Off = FC ? 16 : 0;          // first A column of the layer-2 contraction
-  static constexpr int TileCols = kN + 2 * ACols;    // D | A_hi | A_lo
+  // Split accumulators (nets whose row fits): layer 1 accumulates in D1, layer 2 in D2, so the part of a layer's
+  // contraction whose operand columns are already final (layer 2: the h2 columns, layer 1 of the NEXT step: the h1
+  // columns) is issued one epilogue early and only 9 / 3 of the 18 / 9 MMAs stay on the step's critical path.
+  static constexpr bool SplitD = !FC;
+  static constexpr int DCols = SplitD ? 2 * kN : kN;
+  static constexpr int TileCols = DCols + 2 * ACols;  // D1 [| D2] | A_hi | A_lo
   static constexpr int B1Floats = K1 * kN, B2Floats = K2 * kN;
   static constexpr int ImgFloats = 2 * (B1Floats + B2Floats);
   static constexpr int ImgBytes = ImgFloats * 4;
   static_assert(kTiles * TileCols <= kTmemCols, "TMEM budget");
   static_assert(!FC || C::F == 20, "fc preprocessing: dim 20");
 };
+#ifdef L2O_TC_FDBG
+// progress words in host-mapped memory (scripts/tc_fwd_prof.cu, hang diagnosis): CTA 0 only
+__device__ volatile int* g_fdbg;
+#define L2O_FDBG(slot, val) do { if (blockIdx.x == 0 && g_fdbg) g_fdbg[slot] = (val); } while (0)
+#else
+#define L2O_FDBG(slot, val) do { } while (0)
+#endif
+#ifdef L2O_TC_FPROF
+// timeline instrumentation (scripts/tc_fwd_prof.cu only): clock64 stamps of CTA 0; role 0 / 1 = tile 0 half 0 / half 1
+// (warp 0 / 4, lane 0), 2 = tile 1 half 0 (warp 8), 3 = issuer (tag in the low 3 bits)
+__device__ long long g_fprof[4 * 4096];
+__device__ int g_fprof_n[4];
+#define L2O_FPROF(role, tag) \
+  do { if (blockIdx.x == 0) { int k_ = g_fprof_n[role]; if (k_ < 4096) { g_fprof[(role) * 4096 + k_] = (clock64() << 3) | (tag); g_fprof_n[role] = k_ + 1; } } } while (0)
+#else
+#define L2O_FPROF(role, tag) do { } while (0)
+#endif
 constexpr uint32_t kSBO = 128;               // bytes between 8-row (N) core-matrix groups
 constexpr uint32_t kLBO = (kN / 8) * 128;    // bytes between 16-byte K chunks
 
@@ -92,6 +114,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -273,6 +308,27 @@ __device__ __forceinline__ void store_units(float* __restrict__ p, const float* 
     else *reinterpret_cast<float2*>(p + K0) = make_float2(v[K0], v[K0 + 1]);
   });
 }
+// the same into a shared-window address (explicit st.shared)
+template <int HALF>
+__device__ __forceinline__ void sts_units(uint32_t sa, const float* v) {
+  for_chunks<HALF>([&](auto k0c, auto ncc) {
+    L2O_CHUNK(K0, NC, k0c, ncc);
+    if constexpr (NC == 4) {
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + 4u * K0), "f"(v[K0]), "f"(v[K0 + 1]), "f"(v[K0 + 2]),
+                   "f"(v[K0 + 3])
+                   : "memory");
+    } else {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sa + 4u * K0), "f"(v[K0]), "f"(v[K0 + 1]) : "memory");
+    }
+  });
+}
+// TMA bulk store shared -> global (one thread; bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(float* dst, uint32_t src_s, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -521,6 +577,8 @@ struct Smem {
   uint64_t a_ready[kTiles];
   uint64_t d_ready[kTiles];
   uint64_t full[2], empty[2];     // STAGE: state rows of a tile pair landed in / drained from staging buffer b
+  uint64_t st_ready[kTiles][2];   // staged stores: a tile's new (h, c) rows of layer l are in shared memory (256 arrivals)
+  uint64_t st_free[kTiles][2];    // store warp -> epilogue: the TMA engine has read the layer's staging rows
   uint32_t tmem_slot;
   uint32_t pad;
   double fx[1];                   // [T+1], dynamic tail
@@ -559,7 +617,8 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
   const bool want_fx = in_kernel_opt && a.fx != nullptr;
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
   const uint32_t t_d = tmem_base + lane_off + tile * kTileCols;
-  const uint32_t t_ah = t_d + kN;
+  const uint32_t t_d2 = t_d + (G::SplitD ? kN : 0);   // layer-2 accumulators
+  const uint32_t t_ah = t_d + G::DCols;
   const uint32_t t_al = t_ah + kACols;
   uint32_t pd = 0;  // d_ready parity
   const int64_t slot = n * C::SF;
@@ -571,6 +630,16 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
   const bool adam_mode = C::NIN == 2 && a.m != nullptr;   // fused RNNProp features (DM/meta_rnnprop_train.py:383-388)
   uint32_t pfull[2] = {0, 0};
   int kpair = 0;
+  // Staged stores: with checkpoints (training) or in the step regime every step writes this thread's 2 x NU x 2 new
+  // state values; as float4 stores at an 80-byte row stride a warp-level store touches 20 cache lines, and the LSU
+  // queue backs up on the step's critical path (ncu: mio_throttle 15 %, about 2 K cycles between the pair barrier and the
+  // next step).  Instead the rows go to shared memory (conflict-free st.shared.v4) and a warp of the issuer warpgroup
+  // writes each tile's 10 KB (h | c) blocks with TMA bulk stores.  kTst 1: dedicated staging (single-buffered per layer,
+  // st_free handshake); STAGE: the ring slot the rows were loaded from (same addresses per thread), released to the
+  // producer by the store warp.
+  const bool tst = STAGE || a.ckpt != nullptr;
+  uint32_t pfree[2] = {0, 0};
+  bool staged_before = false;
   // Step-at-a-time regime (STAGE): the parameter and the first input of the NEXT pair are loaded one pair ahead, so
   // their DRAM latency hides behind this pair's two MMA round trips (the state rows already arrive through the TMA ring).
   constexpr bool kAheadIn = STAGE;   // in_seq[i] is the first input of step 0 in every input layout
@@ -625,7 +694,7 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
           load_units_smem<HALF>(sb + 8u * kStageArr, h2);
           load_units_smem<HALF>(sb + 12u * kStageArr, c2);
         }
-        mbar_arrive(&S.empty[buf]);   // release: the producer may refill this buffer (two pairs ahead)
+        // (the slot is reused as the staging area of this pair's stores; the store warp releases it to the producer)
       }
       if (act) {
         if constexpr (!STAGE) {
@@ -646,7 +715,11 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       st_split_units<HALF>(t_ah, t_al, kColH1 + U0, h1);
       st_split_units<HALF>(t_ah, t_al, kColH2 + U0, h2);
     }
+    const int prole = (lane == 0 && (warp == 0 || warp == 4 || warp == 8)) ? (warp == 0 ? 0 : (warp == 4 ? 1 : 2)) : -1;
+    (void)prole;
     for (int t = 0; t < T; ++t) {
+      if (prole >= 0) L2O_FPROF(prole, 0);
+      if (prole >= 0) L2O_FDBG(prole * 4, (kpair << 16) | (t << 4) | 0);
       // ---- gradient + preprocessing -> feature chunk of A (half 1 owns the per-coordinate scalars) ----------
       float fval = 0.f;
       if (HALF == 1) {
@@ -706,6 +779,7 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready[tile]);
+      if (prole >= 0) L2O_FPROF(prole, 1);
       if (HALF == 1 && want_fx) {
         const double ws = warp_sum_d((double)fval);
         if (lane == 0) atomicAdd(&S.fx[t], ws);
@@ -714,6 +788,8 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       mbar_wait(&S.d_ready[tile], pd);
       pd ^= 1;
       tc_fence_after();
+      if (prole >= 0) L2O_FPROF(prole, 2);
+      if (prole >= 0) L2O_FDBG(prole * 4, (kpair << 16) | (t << 4) | 2);
       float hrow[NU];
       {
         float z[4 * NU];  // this thread's 40 gate pre-activations: three loads in flight behind one wait
@@ -729,24 +805,37 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&S.a_ready[tile]);
-      if (act) {
-        if (a.ckpt) {
-          float* ck = a.ckpt + (int64_t)(t + 1) * slot;
-          store_units<HALF>(ck + i * kH + U0, hrow);
-          store_units<HALF>(ck + (n + i) * kH + U0, c1);
+      if (prole >= 0) L2O_FPROF(prole, 3);
+      if (prole >= 0) L2O_FDBG(prole * 4, (kpair << 16) | (t << 4) | 3);
+      // shared address of this thread's slice of the tile's staging block (arrays h1 | c1 | h2 | c2)
+      const uint32_t sst = smem_u32(stage) + 4u * (uint32_t)((((STAGE ? (kpair & 1) : 0) * kTiles + tile) * 4) * kStageArr + row * kH + U0);
+      if (tst) {
+        if (staged_before) {   // the previous layer-1 rows have been read (also keeps this barrier pair in lockstep with
+          mbar_wait(&S.st_free[tile][0], pfree[0]);   // the polling store warp: never more than one phase ahead)
+          pfree[0] ^= 1;
         }
+        if (act) {
+          sts_units<HALF>(sst, hrow);
+          sts_units<HALF>(sst + 4u * kStageArr, c1);
+        }
+        fence_proxy_async();
+        mbar_arrive(&S.st_ready[tile][0]);
+        if (prole >= 0) L2O_FDBG(prole * 4 + 1, (kpair << 16) | (t << 4) | 1);
+      } else if (act) {
         if (t == T - 1) store_units<HALF>(state_out + i * kH + U0, hrow);  // final hidden state of layer 1
       }
       // ---- layer 2 epilogue + output linear + parameter add ---------------------------------
       mbar_wait(&S.d_ready[tile], pd);
       pd ^= 1;
       tc_fence_after();
+      if (prole >= 0) L2O_FPROF(prole, 4);
+      if (prole >= 0) L2O_FDBG(prole * 4, (kpair << 16) | (t << 4) | 4);
       float yp = 0.f;
       {
         float z[4 * NU];
         for_chunks<HALF>([&](auto k0c, auto ncc) {
           L2O_CHUNK(K0, NC, k0c, ncc);
-          tmem_ldn<4 * NC>(t_d + 4 * (U0 + K0), z + 4 * K0);
+          tmem_ldn<4 * NC>(t_d2 + 4 * (U0 + K0), z + 4 * K0);
         });
         tc_wait_ld();
 #pragma unroll
@@ -758,17 +847,29 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
       st_split_units<HALF>(t_ah, t_al, kColH2 + U0, hrow);
       // exchange the output-layer partial sums inside the thread pair (named barrier: the tile's 256 threads)
       S.ypart[tile][HALF][row] = yp;
+      if (prole >= 0) L2O_FPROF(prole, 5);
       asm volatile("bar.sync %0, 256;" ::"r"(1 + tile) : "memory");
+      if (prole >= 0) L2O_FPROF(prole, 6);
+      if (prole >= 0) L2O_FDBG(prole * 4, (kpair << 16) | (t << 4) | 6);
       const float y = (S.ypart[tile][0][row] + S.ypart[tile][1][row]) + S.wo[kH];
       const float d = rt.tanh_output ? tanh_acc(y) * rt.scale : y * rt.scale;
       x += d;
-      if (act) {
-        if (a.ckpt) {
-          float* ck = a.ckpt + (int64_t)(t + 1) * slot + 2 * n * kH;
-          store_units<HALF>(ck + i * kH + U0, hrow);
-          store_units<HALF>(ck + (n + i) * kH + U0, c2);
+      if (tst) {
+        if (staged_before) {
+          mbar_wait(&S.st_free[tile][1], pfree[1]);
+          pfree[1] ^= 1;
         }
-        if (t == T - 1) store_units<HALF>(state_out + 2 * n * kH + i * kH + U0, hrow);  // final hidden state of layer 2
+        if (act) {
+          sts_units<HALF>(sst + 8u * kStageArr, hrow);
+          sts_units<HALF>(sst + 12u * kStageArr, c2);
+        }
+        fence_proxy_async();
+        mbar_arrive(&S.st_ready[tile][1]);
+        if (prole >= 0) L2O_FDBG(prole * 4 + 1, (kpair << 16) | (t << 4) | 2);
+        staged_before = true;
+      }
+      if (act) {
+        if (!tst && t == T - 1) store_units<HALF>(state_out + 2 * n * kH + i * kH + U0, hrow);  // final hidden state of layer 2
         if (HALF == 1) {
           if (a.delta_seq) a.delta_seq[(int64_t)t * n + i] = d;
           if (a.labels) {
@@ -787,7 +888,7 @@ __device__ __forceinline__ void fwd_epilogue(const l2o_unroll_args& a, const Net
           optimizee_eval(a.opt_kind, x, oa, ob, a.opt_alpha, a.opt_fscale, fval, gT);
           if (a.g_rec) a.g_rec[(int64_t)T * n + i] = gT;
         }
-        if (T > 0) {
+        if (T > 0 && !tst) {
           store_units<HALF>(state_out + (n + i) * kH + U0, c1);
           store_units<HALF>(state_out + 2 * n * kH + (n + i) * kH + U0, c2);
         }
@@ -819,6 +920,7 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
   const bool want_fx = a.opt_kind != L2O_OPT_NONE && a.fx != nullptr;
   constexpr int kIssuerWarp = kEpiThreads / 32;
 
+  if (threadIdx.x == 0) L2O_FDBG(30, 1);
   if (want_fx)
     for (int t = threadIdx.x; t <= T; t += blockDim.x) S.fx[t] = 0.0;
   if (threadIdx.x < kH) S.wo[threadIdx.x] = a.theta[C::O_WO + threadIdx.x];
@@ -846,8 +948,14 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
       }
       mbar_init(&S.full[0], 1);
       mbar_init(&S.full[1], 1);
-      mbar_init(&S.empty[0], kEpiThreads);
-      mbar_init(&S.empty[1], kEpiThreads);
+      mbar_init(&S.empty[0], kTiles);   // released by the store warp, once per tile
+      mbar_init(&S.empty[1], kTiles);
+      for (int k = 0; k < kTiles; ++k) {
+        mbar_init(&S.st_ready[k][0], 256);
+        mbar_init(&S.st_ready[k][1], 256);
+        mbar_init(&S.st_free[k][0], 1);
+        mbar_init(&S.st_free[k][1], 1);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -871,6 +979,55 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
     else fwd_epilogue<C, 1, STAGE>(a, rt, S, tmem_base, state_out, warp, lane, stage, adamc);
   } else if (warp > kIssuerWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFwdIssuerRegs));  // idle warps of the issuer warpgroup
+    if (warp == kIssuerWarp + 2 && (STAGE || a.ckpt != nullptr)) {
+      // ---- store warp: per tile the events alternate "layer-1 rows staged" / "layer-2 rows staged"; each becomes two
+      // (at t = T-1 four) 10 KB TMA bulk stores: checkpoint slot t+1 and, after the last step, the state arena
+      const uint32_t sst0 = smem_u32(smem_raw + stage_offset<C>(T));
+      const int64_t slot = n * C::SF;
+      uint32_t ps[kTiles][2] = {{0, 0}, {0, 0}};
+      int k = 0;
+      for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++k) {
+        int ev[kTiles] = {0, 0};
+        while (ev[0] < 2 * T || ev[1] < 2 * T) {
+#pragma unroll
+          for (int tile = 0; tile < kTiles; ++tile) {
+            if (ev[tile] >= 2 * T || !mbar_test(&S.st_ready[tile][ev[tile] & 1], ps[tile][ev[tile] & 1])) continue;
+            const int e = ev[tile]++;
+            const int t = e >> 1, layer = e & 1;
+            ps[tile][layer] ^= 1;
+            if (lane == 0) L2O_FDBG(16 + tile, (k << 16) | e);
+            if (lane == 0) {
+              const int64_t base = pair * kTileCoords + tile * 128;
+              const int64_t cnt = n - base < 0 ? 0 : (n - base > 128 ? 128 : n - base);
+              if (cnt > 0) {
+                const uint32_t bytes = (uint32_t)cnt * kH * 4u;
+                const uint32_t src_h = sst0 + 4u * (uint32_t)((((STAGE ? (k & 1) : 0) * kTiles + tile) * 4 + 2 * layer) * kStageArr);
+                const uint32_t src_c = src_h + 4u * kStageArr;
+                const int64_t loff = (int64_t)layer * 2 * n * kH;
+                if (a.ckpt) {
+                  float* ck = a.ckpt + (int64_t)(t + 1) * slot + loff;
+                  bulk_s2g(ck + base * kH, src_h, bytes);
+                  bulk_s2g(ck + (n + base) * kH, src_c, bytes);
+                }
+                if (t == T - 1) {
+                  bulk_s2g(state_out + loff + base * kH, src_h, bytes);
+                  bulk_s2g(state_out + loff + (n + base) * kH, src_c, bytes);
+                }
+              }
+              bulk_commit();
+              bulk_wait_read0();
+              mbar_arrive(&S.st_free[tile][layer]);
+              L2O_FDBG(18 + tile, (k << 16) | e);
+              if constexpr (STAGE) {
+                if (layer == 1 && t == T - 1) mbar_arrive(&S.empty[k & 1]);   // the ring slot may be refilled
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (lane == 0) bulk_wait0();
+    }
     if constexpr (STAGE) {
       if (warp == kIssuerWarp + 1) {
         // ---- state-row producer: TMA bulk copies of pair k+0, k+1 ... into the two staging buffers -------------------
@@ -922,6 +1079,56 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
     const uint64_t b2l = make_bdesc(img_s + (2 * G::B1Floats + G::B2Floats) * 4);
     constexpr uint64_t kStep = (2 * kLBO) >> 4;  // descriptor start-address increment per K=8 chunk
     uint32_t pa[kTiles] = {0, 0};
+    if constexpr (G::SplitD) {
+      // Polling issuer over the two tiles; per tile the events alternate A(t) (features + h2 final: layer 1's last
+      // K-step, commit, then layer 2's h2 K-steps early) and B(t) (h1' final: layer 2's remaining K-steps, commit, then
+      // the NEXT step's layer-1 h1 K-steps early).  K-step 0 of both layers holds the feature chunk + h1 units 0..3.
+      constexpr int kS1 = G::K1 / 8, kS2 = G::K2 / 8, kS2Early = (G::ColH2 + 7) / 8;   // 3, 6, 3
+      static_assert(G::A2Off == 0 && kS1 == 3 && kS2 == 6 && kS2Early == 3, "split-accumulator schedule: DM row layout");
+      auto kstep = [&](uint32_t d, uint32_t ah, uint32_t al, uint64_t bh, uint64_t bl, int kc, uint32_t acc) {
+        mma_tf32_ts(d, al + 8 * kc, bh + kc * kStep, idesc, acc);
+        mma_tf32_ts(d, ah + 8 * kc, bl + kc * kStep, idesc, 1u);
+        mma_tf32_ts(d, ah + 8 * kc, bh + kc * kStep, idesc, 1u);
+      };
+      for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        int ev[kTiles] = {0, 0};
+        while (ev[0] < 2 * T || ev[1] < 2 * T) {
+#pragma unroll
+          for (int tile = 0; tile < kTiles; ++tile) {
+            if (ev[tile] >= 2 * T || !mbar_test(&S.a_ready[tile], pa[tile])) continue;
+            pa[tile] ^= 1;
+            const int e = ev[tile]++;
+            const int t = e >> 1;
+            if (lane == 0) L2O_FPROF(3, (tile << 1) | (e & 1));
+            if (lane == 0) L2O_FDBG(20 + tile, e);
+            const uint32_t t_d = tmem_base + tile * G::TileCols, t_d2 = t_d + kN;
+            const uint32_t t_ah = t_d + G::DCols, t_al = t_ah + G::ACols;
+            tc_fence_after();
+            if (elect_one()) {
+              if ((e & 1) == 0) {
+                if (t == 0) {   // first step of a pair: nothing was issued ahead
+                  kstep(t_d, t_ah, t_al, b1h, b1l, 1, 0u);
+                  kstep(t_d, t_ah, t_al, b1h, b1l, 2, 1u);
+                }
+                kstep(t_d, t_ah, t_al, b1h, b1l, 0, 1u);
+                tc_commit(&S.d_ready[tile]);
+#pragma unroll
+                for (int kc = kS2Early; kc < kS2; ++kc) kstep(t_d2, t_ah, t_al, b2h, b2l, kc, kc > kS2Early ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int kc = 0; kc < kS2Early; ++kc) kstep(t_d2, t_ah, t_al, b2h, b2l, kc, 1u);
+                tc_commit(&S.d_ready[tile]);
+                if (t + 1 < T) {
+                  kstep(t_d, t_ah, t_al, b1h, b1l, 1, 0u);
+                  kstep(t_d, t_ah, t_al, b1h, b1l, 2, 1u);
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       for (int t = 0; t < T; ++t) {
 #pragma unroll
@@ -929,7 +1136,7 @@ __global__ void __launch_bounds__(kThreads, 1) unroll_fwd_kernel(l2o_unroll_args
 #pragma unroll
           for (int tile = 0; tile < kTiles; ++tile) {
             const uint32_t t_d = tmem_base + tile * G::TileCols;
-            const uint32_t t_ah = t_d + kN;
+            const uint32_t t_ah = t_d + G::DCols;
             const uint32_t t_al = t_ah + G::ACols;
             mbar_wait(&S.a_ready[tile], pa[tile]);
             pa[tile] ^= 1;
@@ -977,7 +1184,10 @@ int tc_launch_fwd(const NetRt& rt, const l2o_unroll_args& a, float* img, cudaStr
   // stage: TMA-prefetched state rows (the l2o_step path, T = 1); needs 16-byte aligned arrays (n * 80 B always is)
   stage = stage && (reinterpret_cast<uintptr_t>(a.state) % 16 == 0);
   auto k = stage ? tc::unroll_fwd_kernel<C, true> : tc::unroll_fwd_kernel<C, false>;
-  const size_t smem = tc::stage_offset<C>(a.T) + (stage ? (size_t)tc::kStageFloats * sizeof(float) : 0) + 128;
+  // + the TMA state ring (step regime) or the staging area of the checkpoint stores (training unroll)
+  const size_t smem = tc::stage_offset<C>(a.T) +
+                      (stage ? (size_t)tc::kStageFloats * sizeof(float)
+                             : (a.ckpt ? (size_t)tc::kTiles * 4 * tc::kStageArr * sizeof(float) : 0)) + 128;
   if (smem > 227 * 1024) return L2O_E_INVALID;
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return L2O_E_CUDA;
   const int64_t npairs = (a.n + tc::kTileCoords - 1) / tc::kTileCoords;
