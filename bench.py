@@ -193,9 +193,16 @@ def external_roofline(prog, netkind, T, t_unroll):
     t_bwd = timed(lambda: h.unroll_bwd(r.net.theta, n, T, in_seq, r.ckpt, dth, g_rec=r.g_rec, **prog._bwd_extra(r)), 3)
     sb, bb = STEP_BYTES[netkind], BWD_BYTES[netkind]
     ach = sb * n / t_step / 1e9
+    step_traffic = None   # measured DRAM bytes of one l2o_step launch (ncu --set full capture of the DM step kernel)
+    if netkind != "rnnprop":
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            step_traffic = tj["step_dram_bytes_per_coord_update"] * n
+        except Exception:
+            pass
     ws = (T + 1) * slot * 4
     return {"bound": "hbm", "kernel": "l2o_step (one coordinate-wise LSTM step, state in HBM)", "achieved": ach,
-            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": step_traffic,
             "algorithmic_bytes_per_coord_update": sb, "step_us": 1e6 * t_step, "coord_updates_per_s_step_kernel": n / t_step,
             "bptt": {"kernel": "l2o_unroll_bwd over the T checkpoint slots", "ms": 1e3 * t_bwd,
                      "algorithmic_bytes_per_coord_update": bb, "achieved": bb * n * T / t_bwd / 1e9,

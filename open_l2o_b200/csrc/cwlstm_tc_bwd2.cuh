@@ -129,6 +129,11 @@ __device__ __forceinline__ void chunks10(const UnitMap& um, F&& f) {
 }
 #define L2O_CHUNK3(K0, NC, k0c, ncc) L2O_CHUNK(K0, NC, k0c, ncc)
 __device__ __forceinline__ void load10(const UnitMap& um, const float* __restrict__ p, float* v) {  // p -> unit 0 of the row
+#ifdef L2O_BWD_NOLOAD   // timing experiment only (scripts/tc_bwd2_prof.cu): how much of a step the strided row loads cost
+#pragma unroll
+  for (int k = 0; k < kNU; ++k) v[k] = 0.01f * (float)(k + 1);
+  return;
+#endif
   chunks10(um, [&](auto k0c, auto ncc, int ub) {
     L2O_CHUNK(K0, NC, k0c, ncc);
     if constexpr (NC == 4) {

@@ -5,13 +5,13 @@ tag=${1:-r02z}
 out=gpurun_out
 mkdir -p $out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $out/${tag}_smoke.log
-timeout 1700 python -m pytest tests -m gpu --maxfail=10 -q --durations=12 --timeout 500 > $out/${tag}_pytest.log 2>&1
+timeout 700 python -m pytest tests -m gpu --maxfail=10 -q --durations=12 --timeout 150 > $out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?" >> $out/${tag}_pytest.log
 grep -E 'passed|failed|FAILED|ERROR|rc=' $out/${tag}_pytest.log | tail -12
 { for n in 65536 1000000; do timeout 300 python scripts/tc_accuracy_large.py $n 100; done; timeout 300 python scripts/tc_accuracy.py; } > $out/${tag}_accuracy.txt 2>&1
 cat $out/${tag}_accuracy.txt
-timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err; echo "ref rc=$?"
-timeout 900 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+timeout 400 python bench.py --impl reference --steps 5 --warmup 2 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err; echo "ref rc=$?"
+timeout 600 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 echo "bench rc=$? capture-warnings: $(grep -c 'capture of the unroll failed' $out/${tag}_bench_n1.err)"
 python - $tag <<'PY'
 import json,sys
