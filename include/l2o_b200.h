@@ -282,6 +282,36 @@ int l2o_hrnn_prepare_finish(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* str
 int l2o_hrnn_step_local(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream);
 int l2o_hrnn_step_finish(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream);
 
+/* Meta-training of the HierarchicalRNN (SC/optimizer/trainable_optimizer.py:200-470: BPTT through the unrolled
+ * optimizer; the optimizee's gradients are stop_gradient'ed, :332-338).  The per-parameter level — everything that
+ * touches N coordinates — is differentiated by l2o_hrnn_coord_bwd; the per-tensor / global GRUs, the 1/RMS(delta)
+ * normalisation, the problem-wide mean log-lr and the objective are [n_tensors x 20]-sized and are differentiated by the
+ * host (open_l2o_b200/hrnn_train.py builds them as torch autograd around these two entry points).
+ *   forward of one step:   write bias0 / zero_flag / mean_log_lr into the workspace (l2o_hrnn_workspace_layout), zero the
+ *                          sums, l2o_hrnn_step_local (planes in place, raw update lr*delta and the per-tensor sums in the
+ *                          workspace);
+ *   backward of that step: l2o_hrnn_coord_bwd with the planes BEFORE the step and the same per-tensor inputs. */
+typedef struct {
+  const float* theta;
+  const float* state_old;    /* [21][N] planes before the step */
+  const float* g;            /* [N] */
+  const float* bias0;        /* [n_tensors][32]: injected gate bias r(10) | u(10) | c(10) | pad, as the forward step used it */
+  const int32_t* zero_flag;  /* [n_tensors][4] */
+  const float* mean_log_lr;  /* [1] */
+  const float* d_state_new;  /* [21][N] adjoints of the planes after the step */
+  const float* d_upd;        /* [N] adjoint of the raw update lr*delta (before the per-tensor 1/RMS) */
+  const float* d_sums;       /* [n_tensors][24] adjoints of the per-tensor sums: h'(10) | feat(12) | delta^2 | log-lr' */
+  float* d_state_old;        /* [21][N] out */
+  double* d_theta;           /* [theta_count] += (the 739 per-parameter-level weights) */
+  double* d_bias0;           /* [n_tensors][32] += */
+  double* d_mean_log_lr;     /* [1] += */
+} l2o_hrnn_bwd_args;
+int l2o_hrnn_coord_bwd(l2o_hrnn_handle h, const l2o_hrnn_bwd_args* a, void* stream);
+/* byte offsets inside the workspace: [0] sums (fp64 [n_tensors][24]) [1] any_nz (int32 [n_tensors][4]) [2] zero_flag
+ * (int32 [n_tensors][4]) [3] bias0 (fp32 [n_tensors][32]) [4] inv_denom (fp32 [n_tensors]) [5] mean_log_lr (fp32 [1])
+ * [6] raw update (fp32 [N]) */
+int l2o_hrnn_workspace_layout(l2o_hrnn_handle h, int64_t offsets[7]);
+
 /* Number of this library's kernels launched so far in this process (bench.py's gpu_launches). */
 int64_t l2o_launch_count(void);
 const char* l2o_status_string(int status);

@@ -31,7 +31,7 @@ EXPORTS = [
     "l2o_hrnn_create", "l2o_hrnn_destroy", "l2o_hrnn_theta_count", "l2o_hrnn_state_floats", "l2o_hrnn_coords",
     "l2o_hrnn_workspace_bytes", "l2o_hrnn_init_state", "l2o_hrnn_prepare", "l2o_hrnn_step",
     "l2o_hrnn_set_global_sizes", "l2o_hrnn_reduce_layout", "l2o_hrnn_prepare_local", "l2o_hrnn_prepare_finish",
-    "l2o_hrnn_step_local", "l2o_hrnn_step_finish",
+    "l2o_hrnn_step_local", "l2o_hrnn_step_finish", "l2o_hrnn_coord_bwd", "l2o_hrnn_workspace_layout",
 ]
 
 
@@ -87,6 +87,12 @@ class DenseBwdArgs(C.Structure):
 class HrnnArgs(C.Structure):
     _fields_ = [("theta", _fp), ("x", _fp), ("g", _fp), ("state", _fp), ("layer", _fp), ("global_", _fp),
                 ("workspace", _fp), ("update", _fp)]
+
+
+class HrnnBwdArgs(C.Structure):
+    _fields_ = [("theta", _fp), ("state_old", _fp), ("g", _fp), ("bias0", _fp), ("zero_flag", _fp), ("mean_log_lr", _fp),
+                ("d_state_new", _fp), ("d_upd", _fp), ("d_sums", _fp), ("d_state_old", _fp), ("d_theta", _fp),
+                ("d_bias0", _fp), ("d_mean_log_lr", _fp)]
 
 
 class L2OError(RuntimeError):
@@ -209,6 +215,10 @@ def lib():
     L.l2o_hrnn_set_global_sizes.restype = C.c_int
     L.l2o_hrnn_reduce_layout.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.l2o_hrnn_reduce_layout.restype = C.c_int
+    L.l2o_hrnn_coord_bwd.argtypes = [C.c_void_p, C.POINTER(HrnnBwdArgs), C.c_void_p]
+    L.l2o_hrnn_coord_bwd.restype = C.c_int
+    L.l2o_hrnn_workspace_layout.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.l2o_hrnn_workspace_layout.restype = C.c_int
     for name in ("l2o_hrnn_init_state", "l2o_hrnn_prepare", "l2o_hrnn_step", "l2o_hrnn_prepare_local",
                  "l2o_hrnn_prepare_finish", "l2o_hrnn_step_local", "l2o_hrnn_step_finish"):
         getattr(L, name).argtypes = [C.c_void_p, C.POINTER(HrnnArgs), C.c_void_p]

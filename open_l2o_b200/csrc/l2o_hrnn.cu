@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(kBlock) coord_kernel(const float* __restrict__
 }
 
 #include "hrnn_tc.cuh"
+#include "hrnn_bwd.cuh"
 
 // state scan used by l2o_hrnn_prepare: per-tensor sum of log-lr and any(ms_i != 0)
 __global__ void __launch_bounds__(kBlock) scan_kernel(const float* __restrict__ state, int64_t n,
@@ -624,6 +625,36 @@ int l2o_hrnn_step_finish(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream
 int l2o_hrnn_step(l2o_hrnn_handle h, const l2o_hrnn_args* a, void* stream) {
   int rc = l2o_hrnn_step_local(h, a, stream);
   return rc ? rc : l2o_hrnn_step_finish(h, a, stream);
+}
+
+int l2o_hrnn_coord_bwd(l2o_hrnn_handle h, const l2o_hrnn_bwd_args* a, void* stream) {
+  if (!h || !a || !a->theta || !a->state_old || !a->g || !a->bias0 || !a->zero_flag || !a->mean_log_lr ||
+      !a->d_state_new || !a->d_upd || !a->d_sums || !a->d_state_old || !a->d_theta || !a->d_bias0 || !a->d_mean_log_lr)
+    return L2O_E_INVALID;
+  bwd::Args k{a->theta, a->state_old, a->g, a->bias0, a->zero_flag, a->mean_log_lr, a->d_state_new, a->d_upd, a->d_sums,
+              a->d_state_old, a->d_theta, a->d_bias0, a->d_mean_log_lr};
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = h->nblocks < 2 * sms ? h->nblocks : 2 * sms;
+  bwd::coord_bwd_kernel<<<grid, bwd::kBwdBlock, 0, (cudaStream_t)stream>>>(k, h->n, h->d_blocks, h->nblocks);
+  L2O_CUDA_TRY(cudaGetLastError());
+  l2o::count_launch();
+  return L2O_OK;
+}
+
+int l2o_hrnn_workspace_layout(l2o_hrnn_handle h, int64_t offsets[7]) {
+  if (!h || !offsets) return L2O_E_INVALID;
+  Workspace w;
+  char* base = (char*)256;   // offsets relative to a dummy non-null base
+  carve(w, base, h->nt, h->n);
+  offsets[0] = (char*)w.acc - base;
+  offsets[1] = (char*)w.any_nz - base;
+  offsets[2] = (char*)w.zero_flag - base;
+  offsets[3] = (char*)w.bias0 - base;
+  offsets[4] = (char*)w.inv_denom - base;
+  offsets[5] = (char*)w.mean_log_lr - base;
+  offsets[6] = (char*)w.upd - base;
+  return L2O_OK;
 }
 
 int l2o_hrnn_set_global_sizes(l2o_hrnn_handle h, const int64_t* global_sizes) {

@@ -1,0 +1,119 @@
+"""Meta-training of the HierarchicalRNN: BPTT through the unrolled optimizer on the engine
+(l2o_hrnn_step_local forward + l2o_hrnn_coord_bwd backward, cross-coordinate pieces as torch autograd) against
+torch.autograd through the fp64 CPU oracle's step (SC/optimizer/trainable_optimizer.py:200-470, 586-609)."""
+import math
+
+import pytest
+import torch
+
+from oracle import hrnn_oracle as orc   # checker only
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _problem(seed=0, dtype=torch.float64, device="cpu"):
+    gen = torch.Generator().manual_seed(seed)
+    A = torch.randn(40, 30, generator=gen, dtype=torch.float64)
+    y = torch.randn(40, 7, generator=gen, dtype=torch.float64)
+    C = torch.randn(150, generator=gen, dtype=torch.float64)
+    A, y, C = A.to(device=device, dtype=dtype), y.to(device=device, dtype=dtype), C.to(device=device, dtype=dtype)
+
+    def objective(params):
+        w, b, v = params
+        return ((A @ w + b - y) ** 2).mean() + 0.1 * ((v - C) ** 2).mean() + 0.01 * torch.cos(3.0 * v).mean()
+    shapes = [(30, 7), (7,), (150,)]
+    init = [torch.randn(s, generator=gen, dtype=torch.float64) * 0.5 for s in shapes]
+    return objective, shapes, init
+
+
+def _oracle_meta_gradient(theta, objective, init, llr, T):
+    th = theta.double().clone().requires_grad_(True)
+    P = orc.unpack_theta(th)
+    gen = torch.Generator().manual_seed(0)
+    params = [p.double() for p in init]
+    states, off = [], 0
+    for p in params:
+        st = orc.initial_state(P, p, gen)
+        st["log_learning_rate"] = llr[off:off + p.numel()].double().reshape(-1, 1)
+        off += p.numel()
+        states.append(st)
+    glob = orc.initial_global_state(P, torch.float64)
+    objs = []
+    for t in range(T):
+        ps = [p.detach().requires_grad_(True) for p in params]
+        f = objective(ps)
+        grads = torch.autograd.grad(f, ps)
+        objs.append(objective(params) if t > 0 else f.detach())
+        params, states, glob, _ = orc.step(th, params, [g.detach() for g in grads], states, glob)
+    allo = torch.stack([o.reshape(()) for o in objs])
+    meta = torch.log(allo / (objs[0].detach() + 1e-6) + 1e-6).mean()
+    g = torch.autograd.grad(meta, th)[0] if meta.requires_grad else torch.zeros_like(th)
+    return float(meta), g.detach(), [float(o) for o in objs], torch.cat([p.detach().reshape(-1) for p in params])
+
+
+def _groups():
+    out, off = [], 0
+    for name, shape in orc.theta_spec():
+        n = int(math.prod(shape))
+        out.append((name, off, off + n))
+        off += n
+    return out
+
+
+@pytest.mark.parametrize("T", [1, 2, 5])
+def test_hrnn_meta_gradient_matches_oracle_autograd(T):
+    from open_l2o_b200 import hrnn_train as ht
+    obj64, shapes, init = _problem(dtype=torch.float64, device="cpu")
+    obj32, _, _ = _problem(dtype=torch.float32, device=DEV)
+    theta = orc.init_theta(seed=3)
+    n = sum(int(math.prod(s)) for s in shapes)
+    llr = (torch.rand(n, generator=torch.Generator().manual_seed(5), dtype=torch.float64) * 3.0 - 6.0).float()
+    meta_ref, g_ref, objs_ref, x_ref = _oracle_meta_gradient(theta, obj64, init, llr, T)
+    tr = ht.MetaTrainer(shapes, theta=theta, device=DEV)
+    meta, g, objs, final = tr.meta_gradient(obj32, [p.float().to(DEV) for p in init], T, log_learning_rate=llr)
+    torch.cuda.synchronize()
+    assert abs(float(meta) - meta_ref) <= 1e-5 * max(1.0, abs(meta_ref)), (float(meta), meta_ref)
+    for a, b in zip(objs, objs_ref):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b)), (objs, objs_ref)
+    assert float((final.x.detach().cpu().double() - x_ref).abs().max()) <= 2e-5 * float(x_ref.abs().max())
+    g = g.detach().cpu().double()
+    scale = float(g_ref.abs().max())
+    if T == 1:      # a one-step unroll has a constant objective: the meta-gradient vanishes identically
+        assert scale == 0.0 and float(g.abs().max()) == 0.0
+        return
+    assert scale > 0
+    worst = []
+    for name, lo, hi in _groups():
+        e = float((g[lo:hi] - g_ref[lo:hi]).abs().max())
+        worst.append((e / scale, name, float(g_ref[lo:hi].abs().max()) / scale))
+    worst.sort(reverse=True)
+    assert worst[0][0] <= 2e-4, worst[:6]
+    # every block of theta that the reference gradient reaches must be reached here too (and vice versa)
+    for name, lo, hi in _groups():
+        ref_nz, got_nz = bool((g_ref[lo:hi] != 0).any()), bool((g[lo:hi] != 0).any())
+        assert ref_nz == got_nz, (name, ref_nz, got_nz)
+
+
+def test_hrnn_meta_training_rmsprop_step_and_descent():
+    """RMSProp with make_finite + clipping (SC/metaopt.py:255-289): the update rule on a known gradient, then a few
+    meta-steps on the toy problem move theta along the negative clipped gradient."""
+    from open_l2o_b200 import hrnn_train as ht
+    obj32, shapes, init = _problem(dtype=torch.float32, device=DEV)
+    tr = ht.MetaTrainer(shapes, theta=orc.init_theta(seed=3), device=DEV, learning_rate=1e-3, gradient_clip=0.5,
+                        random_seed=7)
+    th0 = tr.theta.detach().clone()
+    g = torch.zeros_like(th0)
+    g[0], g[1], g[2], g[3] = 2.0, float("nan"), -0.25, float("inf")
+    used = tr.apply_meta_gradient(g)
+    assert used[0] == 0.5 and used[1] == 0.0 and used[2] == -0.25 and used[3] == 0.0
+    rms = 0.9 * 1.0 + 0.1 * used ** 2                       # accumulator starts at one (tf.train.RMSPropOptimizer)
+    want = th0 - 1e-3 * used / torch.sqrt(rms + 1e-20)
+    assert float((tr.theta.detach() - want).abs().max()) <= 1e-7
+    p0 = [p.float().to(DEV) for p in init]
+    metas = []
+    for _ in range(3):
+        meta, objs, _ = tr.train_step(obj32, p0, 4)
+        assert math.isfinite(meta) and all(math.isfinite(o) for o in objs)
+        metas.append(meta)
+    assert tr.global_step == 4
