@@ -309,12 +309,35 @@ def quick_measure_hrnn(steps, warmup, T=20, batch=128):
     t_step = e0.elapsed_time(e1) / 1e3 / (steps * T)
     out = {"workload": "L2O-Scale HierarchicalRNN [10,20,20], ConvNet 3x32x32 [(3,3,32),(5,5,32)] synthetic batch %d, "
                        "unroll=%d (BASELINE config #4)" % (batch, T),
-           "coords": n, "unroll": T, "mode": "infer (optimizer step; meta-training of the HierarchicalRNN not built)",
+           "coords": n, "unroll": T, "mode": "infer (the optimizer step); meta-training measured under \"meta_train\"",
            "regime": "external-gradient (torch autograd ConvNet forward/backward between l2o_hrnn_step calls; one "
                      "iteration captured as a CUDA graph by HierarchicalRNN.minimize)",
            "value": n * T * steps / t, "unit": "coordinate-updates/s", "ms_per_step": 1e3 * t / steps, "steps": steps,
            "warmup": warmup, "gpu_launches": launches, "last_fx": float(loss),
            "optimizer_step_us": 1e6 * t_step}
+    # meta-training of the optimizer itself on the same optimizee (hrnn_train.MetaTrainer.train_step: T-step unroll,
+    # BPTT through it, clipped RMSProp; SC/optimizer/trainable_optimizer.py:200-470)
+    try:
+        from open_l2o_b200 import hrnn_train as ht
+        tr = ht.MetaTrainer(prob.param_shapes, device=str(dev), random_seed=0)
+        p0 = [p.detach() for p in params]
+        obj_list = lambda ps: prob.objective(ps, data, labels)
+        tr.train_step(obj_list, p0, T)
+        torch.cuda.synchronize()
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            meta = tr.train_step(obj_list, p0, T)[0]
+        e1.record()
+        torch.cuda.synchronize()
+        t_mt = e0.elapsed_time(e1) / 1e3 / reps
+        out["meta_train"] = {"ms_per_meta_step": 1e3 * t_mt, "coordinate_updates_per_s": n * T / t_mt,
+                             "meta_objective": float(meta),
+                             "what": "one unroll of T steps forward (tcgen05 step kernel) + BPTT (l2o_hrnn_coord_bwd, per-tensor "
+                                     "pieces by torch autograd) + RMSProp on the 8,349 optimizer weights; eager, no CUDA graph"}
+        del tr
+    except Exception as ex:   # reported, never fatal for the headline line
+        out["meta_train"] = {"error": repr(ex)[:200]}
     del opt, params
     # HBM roofline of the step on a state that does not fit L2: 16 tensors x 2M coordinates
     sizes = [2_000_000] * 16

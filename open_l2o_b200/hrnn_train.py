@@ -234,7 +234,7 @@ class MetaTrainer(object):
         eng = self.engine
         P = unpack_theta(theta)
         planes, layer, glob, zero_flag, x = state.planes, state.layer, state.global_state, state.zero_flag, state.x
-        tidx, cnt = eng.tensor_index, eng.counts
+        cnt = eng.counts
         objs, total = [], 0.0
         w = [1.0] * num_steps if obj_weights is None else list(obj_weights)
         for t in range(num_steps):
@@ -257,7 +257,10 @@ class MetaTrainer(object):
                                                          zero_flag)
             means = sums[:, :H0 + NF] / cnt[:, None]                        # mean_coords([h' | feat])  (HR:582-587)
             inv = torch.rsqrt(sums[:, H0 + NF] / cnt + 1e-16)               # 1 / RMS(delta)            (HR:621-626)
-            x = x - upd * inv[tidx]                                         # HR:652-653, 404
+            # (per-tensor scalar broadcast as expand + cat: its backward is a handful of segment sums, where the backward
+            # of inv[tensor_index] is a 354 K-way scatter-add into six numbers — 30 ms per step)
+            inv_coord = torch.cat([inv[j:j + 1].expand(n) for j, n in enumerate(eng.sizes)])
+            x = x - upd * inv_coord                                         # HR:652-653, 404
             layer_bias = glob @ P["PerTensor/Layer1_RNN/Affine/Matrix"] + P["PerTensor/Layer1_RNN/Affine/Bias"]
             layer = _bias_gru(means, layer, P["PerTensor/Layer1_RNN/BiasGRUCell/gates/Affine/Matrix"],
                               P["PerTensor/Layer1_RNN/BiasGRUCell/gates/Affine/Bias"],

@@ -88,7 +88,7 @@ def test_hrnn_meta_gradient_matches_oracle_autograd(T):
         e = float((g[lo:hi] - g_ref[lo:hi]).abs().max())
         worst.append((e / scale, name, float(g_ref[lo:hi].abs().max()) / scale))
     worst.sort(reverse=True)
-    assert worst[0][0] <= 2e-4, worst[:6]
+    assert worst[0][0] <= 1e-5, worst[:6]     # measured 1e-7 .. 3e-7 (scripts/hrnn_train_check.py)
     # every block of theta that the reference gradient reaches must be reached here too (and vice versa)
     for name, lo, hi in _groups():
         ref_nz, got_nz = bool((g_ref[lo:hi] != 0).any()), bool((g[lo:hi] != 0).any())
