@@ -8,7 +8,7 @@ is no PyTorch arithmetic on the step path and no CPU fallback.
 
 Scope: the step itself, with the flag set the reference's drivers run
 (SC/metarun.py:154-225,243).  Meta-training of the HierarchicalRNN's own weights (``TrainableOptimizer.train``,
-SC/optimizer/trainable_optimizer.py:200-470: BPTT through this step + RMSProp) is not built yet.
+SC/optimizer/trainable_optimizer.py:200-470: BPTT through this step + RMSProp) lives in ``hrnn_train.py``.
 """
 from __future__ import annotations
 
