@@ -227,7 +227,7 @@ class MetaTrainer(object):
 
     # ---- one unroll ------------------------------------------------------------------------------------------------
     def unroll(self, objective: Callable, state: OptimizerState, num_steps: int, theta: Optional[torch.Tensor] = None,
-               obj_weights: Optional[Sequence[float]] = None):
+               obj_weights: Optional[Sequence[float]] = None, initial_obj: Optional[torch.Tensor] = None):
         """``loop_body`` x num_steps (trainable_optimizer.py:263-401).  Returns (meta objective with its graph, the list
         of objective values, the final OptimizerState with its graph)."""
         theta = self.theta if theta is None else theta
@@ -272,8 +272,9 @@ class MetaTrainer(object):
                              P["Layer2_RNN/BiasGRUCell/candidate/Affine/Bias"],
                              torch.zeros(1, 3 * H2, device=self.device))
             zero_flag = (any_nz == 0).to(torch.int32)
-        initial = objs[0]
-        meta = self.scale_objective(total, torch.stack([o.reshape(()) for o in objs]), initial.detach())
+        # normalised by the objective at the start of the SERIES of partial unrolls (trainable_optimizer.py:438-441)
+        initial = objs[0].detach() if initial_obj is None else initial_obj
+        meta = self.scale_objective(total, torch.stack([o.reshape(()) for o in objs]), initial)
         return meta, objs, OptimizerState(planes, layer, glob, zero_flag, x)
 
     def scale_objective(self, total_obj, all_objs, initial_obj, obj_scale_eps=1e-6):
@@ -286,16 +287,18 @@ class MetaTrainer(object):
 
     # ---- meta step -------------------------------------------------------------------------------------------------
     def meta_gradient(self, objective: Callable, params: Sequence[torch.Tensor], num_steps: int,
-                      log_learning_rate: Optional[torch.Tensor] = None, state: Optional[OptimizerState] = None):
-        """(meta objective, d meta / d theta, objective values, final state) of one unroll from ``params``."""
+                      log_learning_rate: Optional[torch.Tensor] = None, state: Optional[OptimizerState] = None,
+                      initial_obj: Optional[torch.Tensor] = None):
+        """(meta objective, d meta / d theta, objective values, final state) of one unroll — from ``params`` with a fresh
+        optimizer state, or continuing from ``state`` (a detached OptimizerState: truncated BPTT over partial unrolls)."""
         if self.theta.grad is not None:
             self.theta.grad = None
         st = state if state is not None else self.initial_state(params, self.theta, log_learning_rate)
-        meta, objs, final = self.unroll(objective, st, num_steps)
+        meta, objs, final = self.unroll(objective, st, num_steps, initial_obj=initial_obj)
         loss = meta + self.l2_reg * (self.theta ** 2).sum() if self.l2_reg else meta
         # (a one-step unroll scores only f(x_0): constant, no meta-gradient)
         grad = torch.autograd.grad(loss, self.theta)[0] if loss.requires_grad else torch.zeros_like(self.theta)
-        return meta.detach(), grad, [float(o) for o in objs], final
+        return meta.detach(), grad, [float(o.detach()) for o in objs], final
 
     def apply_meta_gradient(self, grad: torch.Tensor):
         """make_finite -> clip -> tf.train.RMSPropOptimizer(lr, decay, epsilon) (SC/metaopt.py:255-289)."""
@@ -305,6 +308,34 @@ class MetaTrainer(object):
             self.theta.sub_(self.learning_rate * g / torch.sqrt(self.rms + self.rms_epsilon))
         self.global_step += 1
         return g
+
+    @staticmethod
+    def detach_state(st: OptimizerState) -> OptimizerState:
+        """The state handed from one partial unroll to the next is a constant of the next unroll's meta-gradient
+        (``init_loop_vars_to_override`` assigned from ``final_loop_vals``, SC/metaopt.py:304,546-563)."""
+        return OptimizerState(st.planes.detach(), st.layer.detach(), st.global_state.detach(), st.zero_flag, st.x.detach())
+
+    def train_problem(self, objective: Callable, params: Sequence[torch.Tensor], num_unrolls: int, unroll_len: int,
+                      log_learning_rate: Optional[torch.Tensor] = None):
+        """One training problem of ``metaopt.train_optimizer`` (SC/metaopt.py:458-613): ``num_unrolls`` partial unrolls of
+        ``unroll_len`` steps, a clipped RMSProp meta-step after each, optimizer and optimizee state carried (detached)
+        from unroll to unroll, objectives normalised by the first unroll's initial objective.  Stops early when the
+        objective is no longer finite (the reference's loop_cond).  Returns (meta objectives, all objective values,
+        final optimizee tensors)."""
+        state, initial, metas, values = None, None, [], []
+        for u in range(num_unrolls):
+            meta, grad, objs, final = self.meta_gradient(objective, params, unroll_len, log_learning_rate, state=state,
+                                                         initial_obj=initial)
+            if not all(math.isfinite(o) for o in objs):
+                break
+            self.apply_meta_gradient(grad)
+            metas.append(float(meta))
+            values.extend(objs)
+            if initial is None:
+                initial = torch.tensor(objs[0], device=self.device)
+            state = self.detach_state(final)
+        out = self._split(state.x) if state is not None else [p.detach() for p in params]
+        return metas, values, out
 
     def train_step(self, objective: Callable, params: Sequence[torch.Tensor], num_steps: int,
                    log_learning_rate: Optional[torch.Tensor] = None):

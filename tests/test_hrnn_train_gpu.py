@@ -27,18 +27,23 @@ def _problem(seed=0, dtype=torch.float64, device="cpu"):
     return objective, shapes, init
 
 
-def _oracle_meta_gradient(theta, objective, init, llr, T):
+def _oracle_meta_gradient(theta, objective, init, llr, T, carry=None, initial_obj=None, want_carry=False):
     th = theta.double().clone().requires_grad_(True)
     P = orc.unpack_theta(th)
     gen = torch.Generator().manual_seed(0)
-    params = [p.double() for p in init]
-    states, off = [], 0
-    for p in params:
-        st = orc.initial_state(P, p, gen)
-        st["log_learning_rate"] = llr[off:off + p.numel()].double().reshape(-1, 1)
-        off += p.numel()
-        states.append(st)
-    glob = orc.initial_global_state(P, torch.float64)
+    if carry is None:
+        params = [p.double() for p in init]
+        states, off = [], 0
+        for p in params:
+            st = orc.initial_state(P, p, gen)
+            st["log_learning_rate"] = llr[off:off + p.numel()].double().reshape(-1, 1)
+            off += p.numel()
+            states.append(st)
+        glob = orc.initial_global_state(P, torch.float64)
+    else:   # truncated BPTT: everything handed over from the previous unroll is a constant
+        params = [p.detach() for p in carry[0]]
+        states = [{k: v.detach() for k, v in st.items()} for st in carry[1]]
+        glob = carry[2].detach()
     objs = []
     for t in range(T):
         ps = [p.detach().requires_grad_(True) for p in params]
@@ -47,9 +52,12 @@ def _oracle_meta_gradient(theta, objective, init, llr, T):
         objs.append(objective(params) if t > 0 else f.detach())
         params, states, glob, _ = orc.step(th, params, [g.detach() for g in grads], states, glob)
     allo = torch.stack([o.reshape(()) for o in objs])
-    meta = torch.log(allo / (objs[0].detach() + 1e-6) + 1e-6).mean()
+    f0 = objs[0].detach() if initial_obj is None else initial_obj
+    meta = torch.log(allo / (f0 + 1e-6) + 1e-6).mean()
     g = torch.autograd.grad(meta, th)[0] if meta.requires_grad else torch.zeros_like(th)
-    return float(meta), g.detach(), [float(o) for o in objs], torch.cat([p.detach().reshape(-1) for p in params])
+    out = (float(meta.detach()), g.detach(), [float(o.detach()) for o in objs],
+           torch.cat([p.detach().reshape(-1) for p in params]))
+    return out + ((params, states, glob),) if want_carry else out
 
 
 def _groups():
@@ -117,3 +125,33 @@ def test_hrnn_meta_training_rmsprop_step_and_descent():
         assert math.isfinite(meta) and all(math.isfinite(o) for o in objs)
         metas.append(meta)
     assert tr.global_step == 4
+
+
+def test_hrnn_truncated_bptt_second_unroll_matches_oracle():
+    """Partial unrolls (SC/metaopt.py:458-613): the second unroll starts from the DETACHED state the first one left and is
+    normalised by the first unroll's initial objective; its meta-gradient against the oracle run the same way."""
+    from open_l2o_b200 import hrnn_train as ht
+    obj64, shapes, init = _problem(dtype=torch.float64, device="cpu")
+    obj32, _, _ = _problem(dtype=torch.float32, device=DEV)
+    theta = orc.init_theta(seed=11)
+    n = sum(int(math.prod(s)) for s in shapes)
+    llr = (torch.rand(n, generator=torch.Generator().manual_seed(6), dtype=torch.float64) * 3.0 - 6.0).float()
+    m1, g1, o1, x1, carry = _oracle_meta_gradient(theta, obj64, init, llr, 3, want_carry=True)
+    m2, g2, o2, x2 = _oracle_meta_gradient(theta, obj64, init, llr, 4, carry=carry, initial_obj=torch.tensor(o1[0]))
+    tr = ht.MetaTrainer(shapes, theta=theta, device=DEV)
+    p0 = [p.float().to(DEV) for p in init]
+    meta1, ga, objs_a, fin = tr.meta_gradient(obj32, p0, 3, log_learning_rate=llr)
+    meta2, gb, objs_b, fin2 = tr.meta_gradient(obj32, p0, 4, state=tr.detach_state(fin),
+                                               initial_obj=torch.tensor(objs_a[0], device=DEV))
+    torch.cuda.synchronize()
+    assert abs(float(meta2) - m2) <= 1e-5 * max(1.0, abs(m2)), (float(meta2), m2)
+    for a, b in zip(objs_b, o2):
+        assert abs(a - b) <= 2e-5 * max(1.0, abs(b))
+    gb = gb.detach().cpu().double()
+    scale = float(g2.abs().max())
+    assert scale > 0 and float((gb - g2).abs().max()) <= 1e-5 * scale, float((gb - g2).abs().max()) / scale
+    # the driver form: two unrolls with a meta-step after each
+    tr2 = ht.MetaTrainer(shapes, theta=theta, device=DEV, learning_rate=1e-4)
+    metas, values, out = tr2.train_problem(obj32, p0, num_unrolls=2, unroll_len=3, log_learning_rate=llr)
+    assert len(metas) == 2 and len(values) == 6 and tr2.global_step == 2
+    assert abs(metas[0] - m1) <= 1e-5 * max(1.0, abs(m1))
