@@ -198,6 +198,20 @@ class HierarchicalRNN(object):
         if self._h is not None:
             self._prepare()
 
+    # ---- meta-training ---------------------------------------------------------------------------------------------
+    def meta_trainer(self, var_list: Sequence[torch.Tensor], **kwargs):
+        """A ``hrnn_train.MetaTrainer`` for optimizees shaped like ``var_list`` that starts from this optimizer's
+        weights (``TrainableOptimizer.train``, SC/optimizer/trainable_optimizer.py:200-470).  ``adopt(trainer)`` copies the
+        trained weights back."""
+        from .hrnn_train import MetaTrainer
+        kwargs.setdefault("init_lr_range", self.init_lr_range)
+        return MetaTrainer([tuple(v.shape) for v in var_list], theta=self.theta, device=str(self.device), **kwargs)
+
+    def adopt(self, trainer):
+        self.theta.copy_(trainer.theta.detach())
+        if self._h is not None:
+            self._prepare()
+
     # ---- slots ---------------------------------------------------------------------------------------------------------
     def _create_slots(self, var_list: Sequence[torch.Tensor]):
         """One slot set per optimizee tensor (trainable_optimizer.py:94-105), laid out as 21 planes over the

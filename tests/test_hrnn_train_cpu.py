@@ -1,0 +1,57 @@
+"""Host-side pieces of the HierarchicalRNN meta-training path that run without a GPU: the theta layout and the small
+torch-level cells must agree with the oracle's (SC/optimizer/rnn_cells.py:46-68, trainable_optimizer.py:586-609)."""
+import math
+
+import pytest
+import torch
+
+from oracle import hrnn_oracle as orc   # checker only
+
+
+def test_theta_views_match_oracle_layout():
+    from open_l2o_b200 import hrnn_train as ht
+    theta = orc.init_theta(seed=2)
+    mine, ref = ht.unpack_theta(theta), orc.unpack_theta(theta)
+    assert list(mine) == list(ref)
+    for k in ref:
+        assert mine[k].shape == ref[k].shape and torch.equal(mine[k], ref[k]), k
+    assert sum(v.numel() for v in mine.values()) == orc.theta_count()
+
+
+def test_bias_gru_cell_matches_oracle_and_is_differentiable():
+    from open_l2o_b200 import hrnn_train as ht
+    g = torch.Generator().manual_seed(0)
+    ni, nh, rows = 22, 20, 5
+    x, h = torch.randn(rows, ni, generator=g, dtype=torch.float64), torch.randn(rows, nh, generator=g, dtype=torch.float64)
+    Wg, bg = torch.randn(ni + nh, 2 * nh, generator=g, dtype=torch.float64), torch.randn(2 * nh, generator=g, dtype=torch.float64)
+    Wc, bc = torch.randn(ni + nh, nh, generator=g, dtype=torch.float64), torch.randn(nh, generator=g, dtype=torch.float64)
+    bias = torch.randn(rows, 3 * nh, generator=g, dtype=torch.float64)
+    Wg.requires_grad_(True)
+    a = ht._bias_gru(x, h, Wg, bg, Wc, bc, bias)
+    b = orc._bias_gru(x, h, Wg, bg, Wc, bc, bias)
+    assert torch.allclose(a, b, rtol=0, atol=1e-15)
+    (ga,) = torch.autograd.grad(a.sum(), Wg, retain_graph=True)
+    (gb,) = torch.autograd.grad(b.sum(), Wg)
+    assert torch.allclose(ga, gb, rtol=0, atol=1e-14)
+
+
+def test_meta_trainer_refuses_to_run_without_cuda():
+    from open_l2o_b200 import hrnn_train as ht
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(Exception):
+        ht.MetaTrainer([(3, 2), (2,)])
+
+
+def test_scale_objective_forms():
+    from open_l2o_b200 import hrnn_train as ht
+    tr = ht.MetaTrainer.__new__(ht.MetaTrainer)     # the formula only: no engine behind it
+    objs, f0 = torch.tensor([4.0, 2.0, 1.0], dtype=torch.float64), torch.tensor(4.0, dtype=torch.float64)
+    tr.use_log_objective, tr.use_numerator_epsilon = True, False
+    want = sum(math.log(v / (4.0 + 1e-6) + 1e-6) for v in (4.0, 2.0, 1.0)) / 3
+    assert abs(float(tr.scale_objective(objs.sum(), objs, f0)) - want) < 1e-12
+    tr.use_numerator_epsilon = True
+    want = sum(math.log((v + 1e-6) / (4.0 + 1e-6)) for v in (4.0, 2.0, 1.0)) / 3
+    assert abs(float(tr.scale_objective(objs.sum(), objs, f0)) - want) < 1e-12
+    tr.use_log_objective = False
+    assert abs(float(tr.scale_objective(objs.sum(), objs, f0)) - 7.0 / (4.0 + 1e-6)) < 1e-12

@@ -155,3 +155,18 @@ def test_hrnn_truncated_bptt_second_unroll_matches_oracle():
     metas, values, out = tr2.train_problem(obj32, p0, num_unrolls=2, unroll_len=3, log_learning_rate=llr)
     assert len(metas) == 2 and len(values) == 6 and tr2.global_step == 2
     assert abs(metas[0] - m1) <= 1e-5 * max(1.0, abs(m1))
+
+
+def test_hierarchical_rnn_meta_trainer_round_trip():
+    """HierarchicalRNN.meta_trainer / adopt: train the optimizer's own weights, then step with them."""
+    from open_l2o_b200 import hierarchical_rnn as hr
+    obj32, shapes, init = _problem(dtype=torch.float32, device=DEV)
+    params = [p.float().to(DEV).requires_grad_(True) for p in init]
+    opt = hr.HierarchicalRNN(random_seed=0, **hr.metarun_flags())
+    tr = opt.meta_trainer(params, learning_rate=1e-4, random_seed=1)
+    before = opt.theta.detach().clone()
+    tr.train_problem(obj32, [p.detach() for p in params], num_unrolls=2, unroll_len=3)
+    opt.adopt(tr)
+    assert not torch.equal(opt.theta, before) and torch.equal(opt.theta, tr.theta.detach())
+    losses = opt.minimize(lambda *ps: obj32(list(ps)), params, 3)
+    assert all(math.isfinite(float(v)) for v in losses)
