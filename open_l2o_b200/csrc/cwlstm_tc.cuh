@@ -14,6 +14,9 @@
 //    Biases ride along as a constant-1 column of A.
 //  * accumulators come back with tcgen05.ld (gate columns interleaved i,j,f,o per hidden unit so one
 //    x16 load = 4 complete units); sigmoid/tanh/c/h/output-linear/x+=delta are fused in the epilogue.
+//  * (round 2) warps of the issuer warpgroup: 16 = polling MMA issuer (split accumulators D1 | D2, K-steps whose
+//    operand columns are already final are issued one epilogue early), 17 = TMA producer of the next pair's state rows
+//    (step regime), 18 = TMA store warp (checkpoint / state rows staged in shared memory by the epilogue threads).
 #pragma once
 #include "cwlstm_common.cuh"
 
@@ -33,7 +36,7 @@ constexpr int kColH2 = kXC + kH;             // A columns of h2: [24, 44)
 constexpr int kACols = 48;                   // 44 used + 4 zero pad columns
 constexpr int kK1 = 24;                      // layer-1 K range: cols [0, 24) = [features | 1 | h1]
 constexpr int kK2 = 48;                      // layer-2 K range: cols [0, 48)  (feature rows zero, 1-col = b2, pad rows zero)
-constexpr int kTileCols = kN + 2 * kACols;   // D | A_hi | A_lo = 176 TMEM columns per tile
+constexpr int kTileCols = kN + 2 * kACols;   // default geometry without split accumulators; kernels use Geo<C>::TileCols
 constexpr int kTmemCols = 512;
 constexpr int kB1Floats = kK1 * kN;          // 1920
 constexpr int kB2Floats = kK2 * kN;          // 3840
