@@ -514,18 +514,27 @@ __global__ void prep_weights_kernel(const float* __restrict__ theta, float* __re
 }
 
 // ------------------------------------------------------------------ epilogue helpers
-// One LSTM unit, pointwise, from the four accumulator columns (pre-activations i, j, f, o) of the unit.  8 MUFU ops
-// (5 ex2 + 3 rcp) instead of the 10 of five separate sigmoid/tanh evaluations: sigma(i) tanh(j) =
-// (1-Ej) / ((1+Ei)(1+Ej)) and tanh(c') sigma(o) likewise share one reciprocal.  The exponents are clamped to 2^63
-// so the shared denominator stays finite (sigma/tanh are saturated to fp32 precision long before that).  The
-// activation pipe is the forward kernel's busiest unit (ncu: XU 50 %).  (Folding the -log2(e) factors into the
-// weight images was measured too: -0.7 % time, 1.5x the d-theta error — not kept.)
+// One LSTM unit, pointwise, from the four accumulator columns (pre-activations i, j, f, o) of the unit.  7 MUFU ops
+// (5 ex2 + 2 rcp) instead of the 10 of five separate sigmoid/tanh evaluations: the whole cell update shares ONE
+// reciprocal,  c' = sigma(f) c + sigma(i) tanh(j) = [c (1+Ei)(1+Ej) + (1-Ej)(1+Ef)] / [(1+Ei)(1+Ej)(1+Ef)],
+// and tanh(c') sigma(o) = (1-Ec) / ((1+Ec)(1+Eo)) another.  The exponents are clamped to 2^40 so the triple product
+// stays finite (sigma / tanh are saturated to 1e-12 there).  The activation pipe is the forward kernel's busiest unit
+// (ncu: XU 62 % with the 8-MUFU form).  -DL2O_MUFU8 restores the two-reciprocal cell update.  (Folding the -log2(e)
+// factors into the weight images was measured too: -0.7 % time, 1.5x the d-theta error — not kept.)
 __device__ __forceinline__ void lstm_point_fwd(float zi, float zj, float zf, float zo, float& c, float& h) {
+#if defined(L2O_MUFU8)
   const float Ei = ex2_approx(fminf(-kLog2e * zi, 63.f));
   const float Ej = ex2_approx(fminf(-2.f * kLog2e * zj, 63.f));
   const float f = rcp_approx(1.0f + ex2_approx(fmaf(-kLog2e, zf, -kLog2e)));
   const float ij = (1.0f - Ej) * rcp_approx((1.0f + Ei) * (1.0f + Ej));
   const float cn = fmaf(f, c, ij);
+#else
+  const float Ei = ex2_approx(fminf(-kLog2e * zi, 40.f));
+  const float Ej = ex2_approx(fminf(-2.f * kLog2e * zj, 40.f));
+  const float Qf = 1.0f + ex2_approx(fminf(fmaf(-kLog2e, zf, -kLog2e), 40.f));
+  const float Pij = (1.0f + Ei) * (1.0f + Ej);
+  const float cn = fmaf(c, Pij, (1.0f - Ej) * Qf) * rcp_approx(Pij * Qf);
+#endif
   c = cn;
   const float Ec = ex2_approx(fminf(-2.f * kLog2e * cn, 63.f));
   const float Eo = ex2_approx(fminf(-kLog2e * zo, 63.f));
