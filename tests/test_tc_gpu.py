@@ -298,3 +298,35 @@ def test_tc_rnnprop_bptt_two_pass_matches_ffma(n, T):
     assert off == h.n_theta
     with pytest.raises(Exception):   # without the hand-over buffer the tcgen05 engine refuses an fc net
         h.unroll_bwd(theta, n, T, feat, ckpt, torch.zeros_like(ref), g_rec=g_rec, delta_seq=dseq)
+
+
+@pytest.mark.gpu
+def test_tc_bptt_tanh_output_net_uses_recorded_deltas():
+    """A tanh-output DM net (DM/networks.py:227-232) on the layer-pipelined tensor-core BPTT: tanh' of the output layer comes
+    from the deltas the forward pass recorded; against the exact-fp32 engine (which recomputes y) on the same checkpoints.
+    Without the recorded deltas the tcgen05 engine refuses such a net."""
+    import dataclasses
+    from open_l2o_b200.engine import ENGINE_FFMA, ENGINE_TC
+    spec = dataclasses.replace(SPECS["dm_logsign"], tanh_output=True, scale=0.5)
+    n, T = 148 * 128 + 61, 6
+    gen = torch.Generator().manual_seed(17)
+    theta = _theta(spec, gain=0.6).to(DEV)
+    from tests.helpers import wild_gradients
+    g_rec = torch.stack([wild_gradients(n, gen) for _ in range(T + 1)]).to(DEV)
+    h = make_handle(spec)
+    h.set_engine(ENGINE_FFMA)
+    arena = h.new_state(n, DEV)
+    ckpt = torch.zeros((T + 1) * h.state_floats * n, device=DEV)
+    dseq = torch.empty(T, n, device=DEV)
+    h.unroll_fwd(theta, n, T, arena, in_seq=g_rec[:T].contiguous(), ckpt=ckpt, delta_seq=dseq)
+    assert float(dseq.abs().max()) > 0.05 * spec.scale     # the output layer is really in its nonlinear range
+    outs = {}
+    for eng in (ENGINE_FFMA, ENGINE_TC):
+        h.set_engine(eng)
+        d = torch.zeros(h.n_theta, dtype=torch.float64, device=DEV)
+        h.unroll_bwd(theta, n, T, g_rec[:T].contiguous(), ckpt, d, g_rec=g_rec, delta_seq=dseq)
+        torch.cuda.synchronize()
+        outs[eng] = d
+    assert rel_err(outs[ENGINE_TC], outs[ENGINE_FFMA]) <= REL_TOL
+    with pytest.raises(Exception):
+        h.unroll_bwd(theta, n, T, g_rec[:T].contiguous(), ckpt, torch.zeros_like(outs[ENGINE_TC]), g_rec=g_rec)
