@@ -342,3 +342,62 @@ class MetaTrainer(object):
         meta, grad, objs, final = self.meta_gradient(objective, params, num_steps, log_learning_rate)
         self.apply_meta_gradient(grad)
         return float(meta), objs, self._split(final.x.detach())
+
+
+def train_optimizer(make_trainer: Callable, problems: Sequence, num_problems: int, num_meta_iterations: int,
+                    num_unroll_func: Callable[[], int], num_partial_unroll_itrs_func: Callable[[], int],
+                    select_random_problems: bool = True, callbacks: Optional[Sequence[Callable]] = None,
+                    fix_unroll: bool = False, fix_unroll_length: int = 20, fix_num_steps: int = 100, seed: int = 0,
+                    out=None):
+    """The sampling loop of ``metaopt.train_optimizer`` (SC/metaopt.py:117-613) around ``MetaTrainer``: ``num_problems``
+    draws of a training problem; on each, ``num_meta_iterations`` optimizee runs, every run a series of partial unrolls
+    (``num_unroll_func()`` unrolls of ``num_partial_unroll_itrs_func()`` steps, or ``fix_num_steps // fix_unroll_length``
+    unrolls of ``fix_unroll_length`` steps with ``fix_unroll``) with a clipped RMSProp meta-step after each unroll.
+
+    problems: sequence of ``(objective, init_fn)`` — ``objective(list of tensors) -> scalar``, ``init_fn() -> list of
+    tensors`` (fresh optimizee parameters for a run).  make_trainer(shapes, theta) -> MetaTrainer (or anything with
+    ``theta`` and ``train_problem``); one trainer per problem shape, theta handed on from problem to problem.
+    Returns (theta, log of (problem index, meta objectives)).  The curriculum / evaluation / checkpoint bookkeeping of the
+    reference driver (SC/metaopt.py:172-176, 613-700) is host-side policy and stays with the caller."""
+    import random
+    rng = random.Random(seed)
+    theta, rms, log, trainers = None, None, [], {}
+    for draw in range(num_problems):
+        k = rng.randrange(len(problems)) if select_random_problems else draw % len(problems)
+        objective, init_fn = problems[k]
+        shapes = tuple(tuple(p.shape) for p in init_fn())
+        if shapes not in trainers:
+            trainers[shapes] = make_trainer(shapes, theta)
+        tr = trainers[shapes]
+        if theta is not None and tr.theta is not theta:   # one set of meta-parameters and one RMSProp accumulator
+            with torch.no_grad():                         # across all problems (SC/metaopt.py:255-260)
+                tr.theta.copy_(theta)
+                if rms is not None and getattr(tr, "rms", None) is not None:
+                    tr.rms.copy_(rms)
+        for _ in range(num_meta_iterations):
+            if fix_unroll:
+                lens = [fix_unroll_length] * (fix_num_steps // fix_unroll_length)
+            else:
+                lens = [num_partial_unroll_itrs_func() for _ in range(num_unroll_func())]
+            params = init_fn()
+            # the reference feeds one unroll length per partial unroll; equal lengths go through train_problem directly
+            if len(set(lens)) <= 1:
+                metas, _, _ = tr.train_problem(objective, params, len(lens), lens[0] if lens else 0)
+            else:
+                metas, state, initial = [], None, None
+                for ln in lens:
+                    meta, grad, objs, final = tr.meta_gradient(objective, params, ln, state=state, initial_obj=initial)
+                    if not all(math.isfinite(o) for o in objs):
+                        break
+                    tr.apply_meta_gradient(grad)
+                    metas.append(float(meta))
+                    initial = torch.tensor(objs[0], device=tr.device) if initial is None else initial
+                    state = tr.detach_state(final)
+            log.append((k, metas))
+            if out is not None:
+                print("problem %d: %d unrolls, meta objective %s" % (k, len(metas), ["%.4f" % m for m in metas]), file=out)
+        theta, rms = tr.theta, getattr(tr, "rms", None)
+        for cb in callbacks or ():
+            cb(draw, k, tr)
+    return theta, log
+

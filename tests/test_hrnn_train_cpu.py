@@ -55,3 +55,36 @@ def test_scale_objective_forms():
     assert abs(float(tr.scale_objective(objs.sum(), objs, f0)) - want) < 1e-12
     tr.use_log_objective = False
     assert abs(float(tr.scale_objective(objs.sum(), objs, f0)) - 7.0 / (4.0 + 1e-6)) < 1e-12
+
+
+def test_train_optimizer_sampling_loop_with_a_stub_trainer():
+    """metaopt.train_optimizer's loop structure (SC/metaopt.py:117-613) on a stub trainer: problem draws, one trainer per
+    optimizee shape, theta handed on between problems, unroll counts from the two callables or the fixed schedule."""
+    from open_l2o_b200 import hrnn_train as ht
+    calls = []
+
+    class Stub(object):
+        device = "cpu"
+
+        def __init__(self, shapes, theta):
+            self.shapes = shapes
+            self.theta = torch.zeros(4) if theta is None else theta.clone()
+
+        def train_problem(self, objective, params, num_unrolls, unroll_len):
+            calls.append((self.shapes, num_unrolls, unroll_len))
+            with torch.no_grad():
+                self.theta += 1.0
+            return [0.0] * num_unrolls, [], params
+
+    problems = [(lambda ps: ps[0].sum(), lambda: [torch.zeros(3, 2)]), (lambda ps: ps[0].sum(), lambda: [torch.zeros(5)])]
+    theta, log = ht.train_optimizer(lambda sh, th: Stub(sh, th), problems, num_problems=4, num_meta_iterations=2,
+                                    num_unroll_func=lambda: 3, num_partial_unroll_itrs_func=lambda: 7,
+                                    select_random_problems=False)
+    assert [c[0] for c in calls] == [((3, 2),)] * 2 + [((5,),)] * 2 + [((3, 2),)] * 2 + [((5,),)] * 2
+    assert all(c[1:] == (3, 7) for c in calls)
+    assert float(theta[0]) == 8.0                      # every run moved the shared theta once, across both trainers
+    assert [k for k, _ in log] == [0, 0, 1, 1, 0, 0, 1, 1] and all(len(m) == 3 for _, m in log)
+    calls.clear()
+    ht.train_optimizer(lambda sh, th: Stub(sh, th), problems[:1], 1, 1, lambda: 0, lambda: 0, fix_unroll=True,
+                       fix_unroll_length=20, fix_num_steps=100)
+    assert calls == [(((3, 2),), 5, 20)]
