@@ -170,3 +170,21 @@ def test_hierarchical_rnn_meta_trainer_round_trip():
     assert not torch.equal(opt.theta, before) and torch.equal(opt.theta, tr.theta.detach())
     losses = opt.minimize(lambda *ps: obj32(list(ps)), params, 3)
     assert all(math.isfinite(float(v)) for v in losses)
+
+
+def test_train_optimizer_loop_on_the_engine():
+    """hrnn_train.train_optimizer with real trainers: two problem shapes, unequal partial-unroll lengths, theta and the
+    RMSProp accumulator handed on between problems."""
+    from open_l2o_b200 import hrnn_train as ht
+    obj_a, shapes_a, init_a = _problem(dtype=torch.float32, device=DEV)
+    tgt = torch.randn(64, device=DEV)
+    problems = [(obj_a, lambda: [p.float().to(DEV) for p in init_a]),
+                (lambda ps: ((ps[0] - tgt) ** 2).mean(), lambda: [torch.zeros(64, device=DEV)])]
+    lens = iter([2, 3, 2, 3, 2, 3, 2, 3])
+    theta0 = orc.init_theta(seed=3)
+    theta, log = ht.train_optimizer(lambda sh, th: ht.MetaTrainer(sh, theta=theta0 if th is None else th, device=DEV,
+                                                                  learning_rate=1e-4, random_seed=0),
+                                    problems, num_problems=2, num_meta_iterations=2, num_unroll_func=lambda: 2,
+                                    num_partial_unroll_itrs_func=lambda: next(lens), select_random_problems=False)
+    assert [k for k, _ in log] == [0, 0, 1, 1] and all(len(m) == 2 and all(math.isfinite(v) for v in m) for _, m in log)
+    assert torch.isfinite(theta).all() and not torch.equal(theta.detach().cpu(), theta0)
