@@ -77,8 +77,6 @@ class _Engine(object):
         self._dummy_x = torch.zeros(N, device=device)
         self._dummy_layer = torch.zeros(nt, H1, device=device)
         self._dummy_global = torch.zeros(H2, device=device)
-        self.tensor_index = torch.repeat_interleave(torch.arange(nt, device=device),
-                                                    torch.tensor(self.sizes, device=device))
         self.counts = torch.tensor(self.sizes, dtype=torch.float32, device=device)
 
     def __del__(self):
@@ -230,6 +228,8 @@ class MetaTrainer(object):
                obj_weights: Optional[Sequence[float]] = None, initial_obj: Optional[torch.Tensor] = None):
         """``loop_body`` x num_steps (trainable_optimizer.py:263-401).  Returns (meta objective with its graph, the list
         of objective values, the final OptimizerState with its graph)."""
+        if num_steps < 1:
+            raise ValueError("an unroll needs at least one step")
         theta = self.theta if theta is None else theta
         eng = self.engine
         P = unpack_theta(theta)
