@@ -74,3 +74,39 @@ def test_hrnn_abi_without_gpu():
     from open_l2o_b200.hierarchical_rnn import THETA_SPEC
     import math
     assert sum(math.prod(s) for _, s in THETA_SPEC) == 8349
+
+
+def _struct_fields(name):
+    """Field names of `typedef struct { ... } name;` in the header, in declaration order."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    m = re.search(r"typedef struct\s*\{([^}]*)\}\s*%s\s*;" % name, src)
+    assert m, name
+    out = []
+    for decl in m.group(1).split(";"):
+        decl = decl.strip()
+        if decl:
+            for part in decl.split(","):     # `float beta1, beta2`
+                out.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1])
+    return out
+
+
+def test_ctypes_structs_follow_the_header_field_order():
+    pairs = [("l2o_bwd_args", _lib.BwdArgs), ("l2o_hrnn_bwd_args", _lib.HrnnBwdArgs), ("l2o_hrnn_args", _lib.HrnnArgs)]
+    for cname, cls in pairs:
+        want = _struct_fields(cname)
+        got = [f[0].rstrip("_") for f in cls._fields_]
+        assert got == want, (cname, got, want)
+
+
+def test_new_entry_points_validate_without_gpu():
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    L = _lib.lib()
+    assert L.l2o_hrnn_coord_bwd(None, None, None) == _lib.L2O_E_INVALID
+    assert L.l2o_hrnn_workspace_layout(None, None) == _lib.L2O_E_INVALID
+    from open_l2o_b200.engine import NetHandle
+    rp = NetHandle(layers=(20, 20), preprocess_name="fc", preprocess_options={"dim": 20}, n_in=2, tanh_output=True)
+    n, T = 1000, 20
+    fwd, bwd = rp.workspace_bytes(n, T)
+    base = 4 * (80 * n * (T + 1) + (T + 1) * n + 2 * T * n) + 8 * rp.n_theta
+    assert bwd == base + 4 * T * n * 21          # + recorded deltas and the [T][n][20] hand-over buffer of the two-pass BPTT
