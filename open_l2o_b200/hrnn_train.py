@@ -316,11 +316,12 @@ class MetaTrainer(object):
         return OptimizerState(st.planes.detach(), st.layer.detach(), st.global_state.detach(), st.zero_flag, st.x.detach())
 
     def train_problem(self, objective: Callable, params: Sequence[torch.Tensor], num_unrolls: int, unroll_len: int,
-                      log_learning_rate: Optional[torch.Tensor] = None):
+                      log_learning_rate: Optional[torch.Tensor] = None, obj_train_max_multiplier: float = -1.0):
         """One training problem of ``metaopt.train_optimizer`` (SC/metaopt.py:458-613): ``num_unrolls`` partial unrolls of
         ``unroll_len`` steps, a clipped RMSProp meta-step after each, optimizer and optimizee state carried (detached)
         from unroll to unroll, objectives normalised by the first unroll's initial objective.  Stops early when the
-        objective is no longer finite (the reference's loop_cond).  Returns (meta objectives, all objective values,
+        objective is no longer finite or (``obj_train_max_multiplier`` > 0) has grown past that multiple of the initial
+        objective (the reference's loop_cond).  Returns (meta objectives, all objective values,
         final optimizee tensors)."""
         state, initial, metas, values = None, None, [], []
         for u in range(num_unrolls):
@@ -328,11 +329,15 @@ class MetaTrainer(object):
                                                          initial_obj=initial)
             if not all(math.isfinite(o) for o in objs):
                 break
+            if initial is None:
+                initial = torch.tensor(objs[0], device=self.device)
+            if obj_train_max_multiplier > 0:   # loop_cond's third clause (trainable_optimizer.py:411-418): the run ends
+                f0 = float(initial)            # once the objective has grown past a multiple of the initial one
+                if max(objs) >= f0 + (obj_train_max_multiplier - 1.0) * abs(f0):
+                    break
             self.apply_meta_gradient(grad)
             metas.append(float(meta))
             values.extend(objs)
-            if initial is None:
-                initial = torch.tensor(objs[0], device=self.device)
             state = self.detach_state(final)
         out = self._split(state.x) if state is not None else [p.detach() for p in params]
         return metas, values, out

@@ -88,3 +88,29 @@ def test_train_optimizer_sampling_loop_with_a_stub_trainer():
     ht.train_optimizer(lambda sh, th: Stub(sh, th), problems[:1], 1, 1, lambda: 0, lambda: 0, fix_unroll=True,
                        fix_unroll_length=20, fix_num_steps=100)
     assert calls == [(((3, 2),), 5, 20)]
+
+
+def test_train_problem_stopping_rules_on_a_stubbed_unroll():
+    """train_problem's control flow without a GPU: carried state, series-wide initial objective, and the two early exits
+    of the reference's loop_cond (non-finite objective; objective above obj_train_max_multiplier x initial)."""
+    from open_l2o_b200 import hrnn_train as ht
+    tr = ht.MetaTrainer.__new__(ht.MetaTrainer)
+    tr.device, tr.shapes, tr.sizes = "cpu", [(2,)], [2]
+    seen, applied = [], []
+    script = iter([[4.0, 3.0], [2.5, 2.0], [30.0, 40.0], [1.0, 1.0]])
+
+    def fake_meta_gradient(objective, params, num_steps, log_learning_rate=None, state=None, initial_obj=None):
+        seen.append((state, None if initial_obj is None else float(initial_obj)))
+        objs = next(script)
+        final = ht.OptimizerState(torch.zeros(21, 2), torch.zeros(1, 20), torch.zeros(1, 20), torch.zeros(1, 4), torch.zeros(2))
+        return torch.tensor(-0.1), torch.ones(3), objs, final
+    tr.meta_gradient = fake_meta_gradient
+    tr.apply_meta_gradient = lambda g: applied.append(1)
+    metas, values, out = tr.train_problem(lambda ps: ps[0].sum(), [torch.zeros(2)], num_unrolls=4, unroll_len=2,
+                                          obj_train_max_multiplier=5.0)
+    assert len(metas) == 2 and values == [4.0, 3.0, 2.5, 2.0] and len(applied) == 2     # third unroll: 30 >= 5 x 4 -> stop
+    assert seen[0] == (None, None) and seen[1][0] is not None and seen[1][1] == 4.0 and seen[2][1] == 4.0
+    script = iter([[4.0, float("nan")]])
+    applied.clear()
+    metas, values, _ = tr.train_problem(lambda ps: ps[0].sum(), [torch.zeros(2)], num_unrolls=3, unroll_len=2)
+    assert metas == [] and values == [] and applied == []
